@@ -1,0 +1,58 @@
+"""ORACLE tooling — seeded parity cases shared by ``make_golden.py`` and ``tests/``.
+
+Each case names a config, a weight seed and the synthetic inputs; everything is
+regenerated from seeds on whatever box runs the tests (weights are ~2 GB fp32 for the
+full config and are never stored), only the reference's *outputs* live in tests/golden/.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from artalk_b200 import config as _cfg
+from artalk_b200 import synthetic
+
+
+@dataclass(frozen=True)
+class Case:
+    name: str
+    cfg_name: str               # "TINY" | "FULL"
+    n_clips: int
+    n_samples: int              # per clip, 16 kHz
+    with_style: bool
+    weight_seed: int = 0
+
+    @property
+    def cfg(self):
+        return getattr(_cfg, self.cfg_name)
+
+    def audio(self) -> torch.Tensor:
+        return synthetic.make_audio(self.n_clips, self.n_samples)
+
+    def style(self) -> Optional[torch.Tensor]:
+        return synthetic.make_style_motion(self.n_clips) if self.with_style else None
+
+
+CASES = {
+    # 5.2 s -> 130 frames -> 2 chunks (second one zero padded: quirk 4), with style
+    "tiny_style": Case("tiny_style", "TINY", 2, 83200, True),
+    # exactly one chunk, null style (app/models.py:71-73)
+    "tiny_null": Case("tiny_null", "TINY", 1, 64000, False),
+    # ragged tail: 4.01 s -> 101 frames -> 2 chunks, 1 useful frame in the second
+    "tiny_ragged": Case("tiny_ragged", "TINY", 1, 64160, True),
+    # full depth, 10 s clip (BASELINE configs[1] per-clip unit): 250 frames, 3 chunks
+    "full_10s": Case("full_10s", "FULL", 1, 160000, True),
+}
+
+FLAME_CASE = dict(seed=7, n_frames=6)
+
+
+def flame_inputs():
+    g = torch.Generator().manual_seed(FLAME_CASE["seed"])
+    n = FLAME_CASE["n_frames"]
+    shape = 0.5 * torch.randn(n, 300, generator=g)
+    motion = 0.3 * torch.randn(n, 106, generator=g)
+    motion[0, 100:] = 0.0           # exact zero rotation exercises the ||r+1e-8|| quirk
+    return shape, motion
