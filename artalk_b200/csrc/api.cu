@@ -1,0 +1,155 @@
+// extern "C" surface of libartalk_b200.so (include/artalk_b200.h).
+#include <cstring>
+#include <new>
+#include "../../include/artalk_b200.h"
+#include "engine.cuh"
+
+using namespace artalk;
+
+namespace artalk { const char* last_error(); }
+
+struct artalk_engine { Engine eng; };
+
+static_assert(sizeof(artalk_config_t) == sizeof(EngineConfig), "artalk_config_t / EngineConfig layout mismatch");
+
+static inline RowMap rm(const artalk_rowmap_t& m) { RowMap r; r.rpb = m.rpb; r.bs = m.bs; r.rs = m.rs; return r; }
+
+extern "C" {
+
+const char* artalk_last_error(void) { return last_error(); }
+int artalk_abi_version(void) { return 1; }
+
+int artalk_create(const artalk_config_t* cfg, artalk_engine_t** out) {
+  AT_REQUIRE(cfg && out, "artalk_create: null argument");
+  artalk_engine* e = new (std::nothrow) artalk_engine();
+  if (!e) return AT_ENOMEM;
+  std::memcpy(&e->eng.cfg, cfg, sizeof(EngineConfig));
+  *out = e;
+  return AT_OK;
+}
+
+int artalk_destroy(artalk_engine_t* e) {
+  if (!e) return AT_OK;
+  if (e->eng.ws) cudaFree(e->eng.ws);
+  delete e;
+  return AT_OK;
+}
+
+int artalk_set_tensor(artalk_engine_t* e, const char* name, void* ptr, int dtype, int64_t numel) {
+  AT_REQUIRE(e, "null engine");
+  return e->eng.set_tensor(name, ptr, dtype, numel);
+}
+int artalk_finalize(artalk_engine_t* e) {
+  AT_REQUIRE(e, "null engine");
+  return e->eng.finalize();
+}
+int artalk_set_workspace_limit(artalk_engine_t* e, size_t bytes) {
+  AT_REQUIRE(e && bytes >= ((size_t)64 << 20), "workspace limit must be >= 64 MiB");
+  e->eng.ws_limit = bytes;
+  return AT_OK;
+}
+size_t artalk_workspace_bytes(const artalk_engine_t* e) { return e ? e->eng.ws_cap : 0; }
+
+int artalk_audio_encode(artalk_engine_t* e, const float* audio, int n_chunks, float* cond, void* stream) {
+  AT_REQUIRE(e && audio && cond && n_chunks >= 0, "artalk_audio_encode: bad argument");
+  return e->eng.audio_encode(audio, n_chunks, cond, (cudaStream_t)stream);
+}
+
+int artalk_style_encode(artalk_engine_t* e, const float* style_motion, int n_clips, float* style, void* stream) {
+  AT_REQUIRE(e && style_motion && style && n_clips >= 0, "artalk_style_encode: bad argument");
+  return e->eng.style_encode(style_motion, n_clips, style, (cudaStream_t)stream);
+}
+
+int artalk_motion_to_bits(artalk_engine_t* e, const float* motion, int n_clips, uint32_t* words, float* enc_out, void* stream) {
+  AT_REQUIRE(e && motion && words && n_clips >= 0, "artalk_motion_to_bits: bad argument");
+  AT_REQUIRE(e->eng.finalized, "engine not finalized");
+  Engine& g = e->eng;
+  const size_t s = dt_size(g.act_dt());
+  size_t need = (size_t)n_clips * g.T * (128 * s + g.cfg.vae_hidden * (4 + 7 * s) + g.cfg.code_dim * 4) + (2 << 20);
+  AT_TRY(g.ws_reserve(need, (cudaStream_t)stream));
+  return g.vae_encode_bits(motion, n_clips, words, enc_out, (cudaStream_t)stream);
+}
+
+int artalk_bits_to_motion(artalk_engine_t* e, const uint32_t* prev_words, const uint32_t* words, int n_clips, float* motion,
+                          void* stream) {
+  AT_REQUIRE(e && prev_words && words && motion && n_clips >= 0, "artalk_bits_to_motion: bad argument");
+  AT_REQUIRE(e->eng.finalized, "engine not finalized");
+  Engine& g = e->eng;
+  const size_t s = dt_size(g.act_dt());
+  size_t need = (size_t)n_clips * 2 * g.T * (g.cfg.code_dim * s + g.cfg.vae_hidden * (4 + 7 * s)) + (2 << 20);
+  AT_TRY(g.ws_reserve(need, (cudaStream_t)stream));
+  return g.vae_decode(prev_words, words, n_clips, motion, (cudaStream_t)stream);
+}
+
+int artalk_ar_chunk(artalk_engine_t* e, int n_clips, const float* cond, int64_t cond_clip_stride, const float* style,
+                    uint32_t* prev_words, float* motion_out, uint32_t* words_out, float* logits_out,
+                    const uint32_t* forced_words, float* enc_out, void* stream) {
+  AT_REQUIRE(e && cond && style && prev_words && motion_out && n_clips >= 0, "artalk_ar_chunk: bad argument");
+  return e->eng.ar_chunk(n_clips, cond, cond_clip_stride, style, prev_words, motion_out, words_out, logits_out, forced_words,
+                         enc_out, (cudaStream_t)stream);
+}
+
+static FlameModel to_flame(const artalk_flame_model_t* f) {
+  FlameModel m;
+  m.V = f->n_verts; m.n_shape = f->n_shape; m.n_exp = f->n_exp; m.v_template = f->v_template; m.dirs = f->dirs;
+  m.j_template = f->j_template; m.j_dirs = f->j_dirs; m.lbs_weights = f->lbs_weights;
+  for (int i = 0; i < 5; ++i) m.parents[i] = f->parents[i];
+  m.scale = f->scale;
+  return m;
+}
+
+size_t artalk_flame_workspace_floats(const artalk_flame_model_t* fm, int n_frames) {
+  if (!fm || n_frames < 0) return 0;
+  return flame_workspace_floats(to_flame(fm), n_frames);
+}
+
+int artalk_flame_vertices(const artalk_flame_model_t* fm, const float* shape, int64_t shape_stride, const float* expr,
+                          int64_t expr_stride, const float* pose, int64_t pose_stride, int zero_global, float* workspace,
+                          float* verts, int n_frames, void* stream) {
+  AT_REQUIRE(fm && shape && expr && pose && workspace && verts && n_frames >= 0, "artalk_flame_vertices: bad argument");
+  AT_REQUIRE(fm->parents[0] < 0, "flame: joint 0 must be the root");
+  for (int j = 1; j < 5; ++j) AT_REQUIRE(fm->parents[j] >= 0 && fm->parents[j] < j, "flame: parents must precede children");
+  return launch_flame(to_flame(fm), shape, shape_stride, expr, expr_stride, pose, pose_stride, zero_global, workspace, verts,
+                      n_frames, (cudaStream_t)stream);
+}
+
+int artalk_set_savgol_tables(const float* host_h5, const float* host_h9) {
+  AT_REQUIRE(host_h5 && host_h9, "null tables");
+  set_savgol_tables(host_h5, host_h9);
+  return AT_OK;
+}
+
+int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_frames, int n_frames_out, int fix_pose,
+                         int zero_tail, void* stream) {
+  AT_REQUIRE(motion && out, "artalk_smooth_motion: null argument");
+  return launch_savgol_post(motion, out, n_clips, n_frames, n_frames_out, 106, fix_pose, zero_tail, (cudaStream_t)stream);
+}
+
+int artalk_op_gemm(const artalk_gemm_t* a, int precision, void* stream) {
+  AT_REQUIRE(a, "null gemm");
+  GemmArgs g = gemm_args();
+  g.A = a->A; g.a_map = rm(a->a_map); g.W = a->W; g.ldw = a->ldw; g.M = a->M; g.N = a->N; g.K = a->K;
+  g.tap_w = a->tap_w; g.tap_pad = a->tap_pad; g.groups = a->groups > 0 ? a->groups : 1;
+  g.a_gs = a->a_gs; g.w_gs = a->w_gs; g.c_gs = a->c_gs; g.bias_gs = a->bias_gs;
+  g.bias = a->bias; g.act = a->act; g.gate = a->gate; g.gate_dt = a->gate_dt; g.gate_map = rm(a->gate_map);
+  g.resid = a->resid; g.resid_map = rm(a->resid_map); g.out32 = a->out32; g.out_act = a->out_act; g.out_act_dt = a->out_act_dt;
+  g.c_map = rm(a->c_map);
+  return precision == ARTALK_PRECISION_FP32 ? launch_gemm_simt(g, (cudaStream_t)stream) : launch_gemm_tc(g, (cudaStream_t)stream);
+}
+
+int artalk_op_attention(const artalk_attn_t* a, void* stream) {
+  AT_REQUIRE(a, "null attn");
+  AttnArgs x;
+  x.q = a->q; x.k = a->k; x.v = a->v; x.out = a->out; x.dt = a->dt; x.n_seq = a->n_seq; x.n_heads = a->n_heads;
+  x.head_dim = a->head_dim; x.lq = a->lq; x.lk = a->lk; x.q_ss = a->q_ss; x.q_rs = a->q_rs; x.k_ss = a->k_ss; x.k_rs = a->k_rs;
+  x.v_ss = a->v_ss; x.v_rs = a->v_rs; x.o_ss = a->o_ss; x.o_rs = a->o_rs; x.scale = a->scale; x.split = a->split;
+  return launch_attention(x, (cudaStream_t)stream);
+}
+
+int artalk_op_layernorm(const float* x, void* out, int out_dt, const float* gamma, const float* beta, int rows, int cols,
+                        float eps, int act, void* stream) {
+  AT_REQUIRE(x && out, "null argument");
+  return launch_layernorm(x, cols, out, out_dt, cols, gamma, beta, rows, cols, eps, act, (cudaStream_t)stream);
+}
+
+}  // extern "C"

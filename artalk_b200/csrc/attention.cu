@@ -1,0 +1,183 @@
+// Short-sequence multi-head attention (<= a few hundred keys, head_dim 32/64) in fp32 arithmetic with
+// flash-style online softmax, plus the AR block's q/k L2-normalise + KV-cache scatter.
+// Covers wav2vec2 self-attention (transformers modeling_wav2vec2.py:466-549), AR ModifiedSelfAttention
+// (app/transformer.py:65-79; mask-free in the KV-cached schedule), VAE SimpleSelfAttention with the 2-block mask
+// (app/modules/bitwise_vae.py:67-76,194-215) and the style encoder's nn.MultiheadAttention.
+#include "kernels.cuh"
+
+namespace artalk {
+
+namespace {
+constexpr int KT = 64;        // keys per shared-memory tile
+constexpr int RPW = 4;        // query rows per warp (register blocking)
+constexpr int WARPS = 4;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(WARPS * 32) attn_kernel(AttnArgs a) {
+  constexpr int DPL = D / 32;                 // output dims per lane
+  __shared__ float Ks[KT][D + 1];
+  __shared__ __align__(16) float Vs[KT][D];
+  __shared__ __align__(16) float Qs[WARPS][D][RPW];
+  __shared__ __align__(16) float Ps[WARPS][KT][RPW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int q0 = blockIdx.x * (WARPS * RPW) + warp * RPW;
+  const T* qb = reinterpret_cast<const T*>(a.q) + (int64_t)seq * a.q_ss + head * D;
+  const T* kb = reinterpret_cast<const T*>(a.k) + (int64_t)seq * a.k_ss + head * D;
+  const T* vb = reinterpret_cast<const T*>(a.v) + (int64_t)seq * a.v_ss + head * D;
+
+  // stage this warp's RPW query rows (pre-scaled) as Qs[d][r]
+  int lk_r[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    int qi = q0 + r;
+    lk_r[r] = (a.split > 0 && qi < a.split) ? a.split : a.lk;
+    for (int d = lane; d < D; d += 32)
+      Qs[warp][d][r] = (qi < a.lq) ? to_f32(qb[(int64_t)qi * a.q_rs + d]) * a.scale : 0.f;
+  }
+  // keys needed by any row of the block
+  int blk_q_last = min(a.lq, (int)(blockIdx.x + 1) * (WARPS * RPW)) - 1;
+  int lk_blk = (a.split > 0 && blk_q_last < a.split) ? a.split : a.lk;
+
+  float m[RPW], l[RPW], acc[RPW][DPL];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    m[r] = -INFINITY; l[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) acc[r][j] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < lk_blk; k0 += KT) {
+    __syncthreads();
+    // cooperative tile load, 4 elements per access
+    for (int i = tid; i < KT * (D / 4); i += WARPS * 32) {
+      int key = i / (D / 4), d4 = (i - key * (D / 4)) * 4;
+      float kv[4] = {0.f, 0.f, 0.f, 0.f}, vv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k0 + key < lk_blk) {
+        load4(kb + (int64_t)(k0 + key) * a.k_rs + d4, kv);
+        load4(vb + (int64_t)(k0 + key) * a.v_rs + d4, vv);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { Ks[key][d4 + j] = kv[j]; Vs[key][d4 + j] = vv[j]; }
+    }
+    __syncthreads();
+    // scores for keys (lane, lane + 32) x RPW rows
+    float s[RPW][2];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) s[r][0] = s[r][1] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) {
+      float4 q4 = *reinterpret_cast<const float4*>(&Qs[warp][d][0]);
+      float ka = Ks[lane][d], kc = Ks[lane + 32][d];
+      s[0][0] = fmaf(q4.x, ka, s[0][0]); s[0][1] = fmaf(q4.x, kc, s[0][1]);
+      s[1][0] = fmaf(q4.y, ka, s[1][0]); s[1][1] = fmaf(q4.y, kc, s[1][1]);
+      s[2][0] = fmaf(q4.z, ka, s[2][0]); s[2][1] = fmaf(q4.z, kc, s[2][1]);
+      s[3][0] = fmaf(q4.w, ka, s[3][0]); s[3][1] = fmaf(q4.w, kc, s[3][1]);
+    }
+    float p[RPW][2];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      if (k0 + lane >= lk_r[r]) s[r][0] = -INFINITY;
+      if (k0 + lane + 32 >= lk_r[r]) s[r][1] = -INFINITY;
+      float tmax = warp_max(fmaxf(s[r][0], s[r][1]));
+      float m_new = fmaxf(m[r], tmax);
+      float corr, p0, p1;
+      if (m_new == -INFINITY) { corr = 1.f; p0 = p1 = 0.f; }      // row sees no key in this tile yet
+      else { corr = __expf(m[r] - m_new); p0 = __expf(s[r][0] - m_new); p1 = __expf(s[r][1] - m_new); }
+      l[r] = l[r] * corr + warp_sum(p0 + p1);
+      m[r] = m_new;
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) acc[r][j] *= corr;
+      p[r][0] = p0; p[r][1] = p1;
+    }
+    *reinterpret_cast<float4*>(&Ps[warp][lane][0]) = make_float4(p[0][0], p[1][0], p[2][0], p[3][0]);
+    *reinterpret_cast<float4*>(&Ps[warp][lane + 32][0]) = make_float4(p[0][1], p[1][1], p[2][1], p[3][1]);
+    __syncwarp();
+    int kmax = min(KT, lk_blk - k0);
+    for (int key = 0; key < kmax; ++key) {
+      float4 p4 = *reinterpret_cast<const float4*>(&Ps[warp][key][0]);
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) {
+        float vv = Vs[key][lane + 32 * j];
+        acc[0][j] = fmaf(p4.x, vv, acc[0][j]);
+        acc[1][j] = fmaf(p4.y, vv, acc[1][j]);
+        acc[2][j] = fmaf(p4.z, vv, acc[2][j]);
+        acc[3][j] = fmaf(p4.w, vv, acc[3][j]);
+      }
+    }
+    __syncwarp();
+  }
+  T* ob = reinterpret_cast<T*>(a.out) + (int64_t)seq * a.o_ss + head * D;
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    int qi = q0 + r;
+    if (qi >= a.lq) continue;
+    float inv = 1.0f / l[r];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) ob[(int64_t)qi * a.o_rs + lane + 32 * j] = from_f32<T>(acc[r][j] * inv);
+  }
+}
+}  // namespace
+
+int launch_attention(const AttnArgs& a, cudaStream_t st) {
+  if (a.n_seq <= 0 || a.lq <= 0) return AT_OK;
+  AT_REQUIRE(a.head_dim == 64 || a.head_dim == 32, "attention: head_dim %d", a.head_dim);
+  AT_REQUIRE(a.lk > 0 && a.k_rs % 4 == 0 && a.v_rs % 4 == 0 && a.k_ss % 4 == 0 && a.v_ss % 4 == 0,
+             "attention: key/value strides must be multiples of 4");
+  dim3 grid(ceil_div(a.lq, WARPS * RPW), a.n_heads, a.n_seq);
+  if (a.dt == DT_F32) {
+    if (a.head_dim == 64) attn_kernel<float, 64><<<grid, WARPS * 32, 0, st>>>(a);
+    else attn_kernel<float, 32><<<grid, WARPS * 32, 0, st>>>(a);
+  } else {
+    if (a.head_dim == 64) attn_kernel<bf16, 64><<<grid, WARPS * 32, 0, st>>>(a);
+    else attn_kernel<bf16, 32><<<grid, WARPS * 32, 0, st>>>(a);
+  }
+  AT_LAUNCH_CHECK();
+  return AT_OK;
+}
+
+// ---------------------------------------------------------------- q/k L2-normalise + KV-cache scatter
+// One warp per (row, head): lane owns 2 of the 64 head dims. F.normalize: x / max(||x||, 1e-12).
+template <typename T>
+__global__ void __launch_bounds__(256) qkv_norm_scatter_kernel(const T* __restrict__ qkv, int64_t qkv_rs, int has_q,
+                                                               const float* __restrict__ head_scale, T* __restrict__ qbuf,
+                                                               T* __restrict__ kcache, T* __restrict__ vcache, RowMap kv_map,
+                                                               int rows, int n_heads) {
+  int C = n_heads * 64;
+  int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (gw >= (int64_t)rows * n_heads) return;
+  int r = (int)(gw / n_heads), h = (int)(gw - (int64_t)r * n_heads);
+  const T* src = qkv + (int64_t)r * qkv_rs + h * 64 + lane * 2;
+  int64_t dst = kv_map.off(r) + h * 64 + lane * 2;
+  int koff = has_q ? C : 0;
+  if (has_q) {
+    float q0 = to_f32(src[0]), q1 = to_f32(src[1]);
+    float n = sqrtf(warp_sum(q0 * q0 + q1 * q1));
+    float sc = head_scale[h] / fmaxf(n, 1e-12f);
+    T* qd = qbuf + (int64_t)r * C + h * 64 + lane * 2;
+    qd[0] = from_f32<T>(q0 * sc); qd[1] = from_f32<T>(q1 * sc);
+  }
+  float k0 = to_f32(src[koff]), k1 = to_f32(src[koff + 1]);
+  float n = sqrtf(warp_sum(k0 * k0 + k1 * k1));
+  float sc = 1.0f / fmaxf(n, 1e-12f);
+  kcache[dst] = from_f32<T>(k0 * sc); kcache[dst + 1] = from_f32<T>(k1 * sc);
+  vcache[dst] = src[koff + C]; vcache[dst + 1] = src[koff + C + 1];
+}
+
+int launch_qkv_norm_scatter(const void* qkv, int dt, int64_t qkv_rs, int has_q, const float* head_scale, void* qbuf,
+                            void* kcache, void* vcache, RowMap kv_map, int rows, int n_heads, cudaStream_t st) {
+  if (rows <= 0) return AT_OK;
+  int64_t warps = (int64_t)rows * n_heads;
+  int grid = (int)((warps + 7) / 8);
+  if (dt == DT_F32)
+    qkv_norm_scatter_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, qkv_rs, has_q, head_scale, (float*)qbuf,
+                                                         (float*)kcache, (float*)vcache, kv_map, rows, n_heads);
+  else
+    qkv_norm_scatter_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, qkv_rs, has_q, head_scale, (bf16*)qbuf,
+                                                        (bf16*)kcache, (bf16*)vcache, kv_map, rows, n_heads);
+  AT_LAUNCH_CHECK();
+  return AT_OK;
+}
+
+}  // namespace artalk

@@ -1,0 +1,133 @@
+// Shared device/host helpers for the artalk_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace artalk {
+
+typedef __nv_bfloat16 bf16;
+
+// status codes of the C ABI (include/artalk_b200.h)
+enum : int { AT_OK = 0, AT_EINVAL = 1, AT_ECUDA = 2, AT_ENOMEM = 3, AT_EMISSING = 4, AT_ESTATE = 5 };
+
+void set_last_error(const char* fmt, ...);
+
+#define AT_CUDA(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::artalk::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                 \
+                               cudaGetErrorString(_e));                                      \
+      return ::artalk::AT_ECUDA;                                                             \
+    }                                                                                        \
+  } while (0)
+
+#define AT_LAUNCH_CHECK() AT_CUDA(cudaGetLastError())
+
+#define AT_REQUIRE(cond, ...)                                                                \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      ::artalk::set_last_error(__VA_ARGS__);                                                 \
+      return ::artalk::AT_EINVAL;                                                            \
+    }                                                                                        \
+  } while (0)
+
+#define AT_TRY(expr)                                                                         \
+  do {                                                                                       \
+    int _s = (expr);                                                                         \
+    if (_s != ::artalk::AT_OK) return _s;                                                    \
+  } while (0)
+
+// row r of a logical [rows, cols] matrix lives at base + (r / rpb) * bs + (r % rpb) * rs (elements)
+struct RowMap {
+  int rpb;        // rows per batch (<=0: plain, offset = r * rs)
+  int64_t bs;     // batch stride
+  int64_t rs;     // row stride
+  __host__ __device__ inline int64_t off(int r) const {
+    if (rpb <= 0) return (int64_t)r * rs;
+    int b = r / rpb;
+    return (int64_t)b * bs + (int64_t)(r - b * rpb) * rs;
+  }
+};
+static inline RowMap plain_rows(int64_t rs) { RowMap m; m.rpb = 0; m.bs = 0; m.rs = rs; return m; }
+static inline RowMap batched_rows(int rpb, int64_t bs, int64_t rs) { RowMap m; m.rpb = rpb; m.bs = bs; m.rs = rs; return m; }
+
+enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_LEAKY02 = 3, ACT_SILU = 4 };
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_GELU_ERF: return gelu_erf(x);
+    case ACT_GELU_TANH: return gelu_tanh(x);
+    case ACT_LEAKY02: return x > 0.f ? x : 0.2f * x;
+    case ACT_SILU: return silu(x);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (multiple of 32); `red` is >= 32 floats of shared memory
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+// 4-wide vector access helpers (fp32: 16 B, bf16: 8 B)
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t align_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace artalk

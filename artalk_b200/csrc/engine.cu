@@ -1,0 +1,565 @@
+// Forward passes of the audio->motion path, scheduled B200-first:
+//  * wav2vec2 over all chunks of all clips up-front (independent of the AR state), in sub-batches;
+//  * the AR recurrence with a KV cache across the 5 scale steps (only the new tokens of a scale are computed; the
+//    cached schedule needs no attention mask), AdaLN parameters for all 12 blocks + head hoisted to one GEMM per chunk,
+//    previous-chunk K/V for all 12 blocks in one GEMM per chunk;
+//  * VAE decode + re-encode + residual BSQ per chunk.
+// Reference semantics: app/models.py:62-121, app/transformer.py:30-79, app/modules/bitwise_vae.py, HF wav2vec2.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "engine.cuh"
+
+namespace artalk {
+
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static std::string S(const char* fmt, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return std::string(buf);
+}
+
+// ------------------------------------------------------------------ registry
+int Engine::set_tensor(const char* name, void* ptr, int dt, int64_t numel) {
+  AT_REQUIRE(name && ptr && numel > 0, "set_tensor: bad argument for '%s'", name ? name : "?");
+  AT_REQUIRE(((uintptr_t)ptr) % 16 == 0, "set_tensor: '%s' must be 16-byte aligned", name);
+  Tensor t; t.ptr = ptr; t.dt = dt; t.numel = numel;
+  tensors[name] = t;
+  finalized = false;
+  return AT_OK;
+}
+
+const Tensor* Engine::find(const std::string& name) const {
+  auto it = tensors.find(name);
+  return it == tensors.end() ? nullptr : &it->second;
+}
+
+int Engine::finalize() {
+  const EngineConfig& c = cfg;
+  AT_REQUIRE(c.precision == 0 || c.precision == 1, "precision must be 0 (fp32) or 1 (bf16)");
+  AT_REQUIRE(c.embed_dim == 768 && c.embed_dim / c.ar_heads == 64, "AR width must be 768 with 64-d heads");
+  AT_REQUIRE(c.vae_hidden == 512 && c.vae_hidden / c.vae_heads == 64, "VAE width must be 512 with 64-d heads");
+  AT_REQUIRE(c.code_dim == 32 && c.motion_dim == 106, "code_dim 32 / motion_dim 106 expected");
+  AT_REQUIRE(c.w2v_hidden == 1024 && c.w2v_conv_dim == 512 && c.w2v_hidden / c.w2v_heads == 64, "wav2vec dims");
+  AT_REQUIRE(c.n_levels >= 2 && c.n_levels <= 8, "n_levels");
+  AT_REQUIRE(c.style_dim == 128 && c.style_dim / c.style_heads == 32, "style encoder dims");
+  const int wt = act_dt();
+  struct Need { std::string name; int dt; int64_t numel; };
+  std::vector<Need> need;
+  auto req = [&](const std::string& n, int dt, int64_t numel) { need.push_back({n, dt, numel}); };
+  L = 0;
+  for (int i = 0; i < c.n_levels; ++i) L += c.patch_nums[i];
+  T = c.patch_nums[c.n_levels - 1];
+  int len = c.chunk_samples;
+  for (int i = 0; i < c.w2v_n_conv; ++i) { len = (len - c.w2v_conv_kernel[i]) / c.w2v_conv_stride[i] + 1; conv_len[i] = len; }
+  n_audio_frames = len;
+  const int CD = c.w2v_conv_dim, H = c.w2v_hidden, C = c.embed_dim, VH = c.vae_hidden;
+  // wav2vec
+  req("w2v.conv0.w", DT_F32, (int64_t)c.w2v_conv_kernel[0] * CD);
+  for (int i = 0; i < c.w2v_n_conv; ++i) {
+    if (i) req(S("w2v.conv%d.w", i), wt, (int64_t)CD * c.w2v_conv_kernel[i] * CD);
+    req(S("w2v.conv%d.b", i), DT_F32, CD); req(S("w2v.conv%d.ln_g", i), DT_F32, CD); req(S("w2v.conv%d.ln_b", i), DT_F32, CD);
+  }
+  req("w2v.proj.ln_g", DT_F32, CD); req("w2v.proj.ln_b", DT_F32, CD);
+  req("w2v.proj.w", wt, (int64_t)H * CD); req("w2v.proj.b", DT_F32, H);
+  req("w2v.pos.w", wt, (int64_t)H * (H / c.w2v_pos_groups) * c.w2v_pos_kernel); req("w2v.pos.b", DT_F32, H);
+  req("w2v.enc_ln_g", DT_F32, H); req("w2v.enc_ln_b", DT_F32, H);
+  for (int l = 0; l < c.w2v_layers; ++l) {
+    req(S("w2v.l%d.ln1_g", l), DT_F32, H); req(S("w2v.l%d.ln1_b", l), DT_F32, H);
+    req(S("w2v.l%d.qkv.w", l), wt, (int64_t)3 * H * H); req(S("w2v.l%d.qkv.b", l), DT_F32, 3 * H);
+    req(S("w2v.l%d.out.w", l), wt, (int64_t)H * H); req(S("w2v.l%d.out.b", l), DT_F32, H);
+    req(S("w2v.l%d.ln2_g", l), DT_F32, H); req(S("w2v.l%d.ln2_b", l), DT_F32, H);
+    req(S("w2v.l%d.ff1.w", l), wt, (int64_t)c.w2v_ffn * H); req(S("w2v.l%d.ff1.b", l), DT_F32, c.w2v_ffn);
+    req(S("w2v.l%d.ff2.w", l), wt, (int64_t)H * c.w2v_ffn); req(S("w2v.l%d.ff2.b", l), DT_F32, H);
+  }
+  // AR
+  const int n_ada = c.ar_depth * 6 * C + 2 * C;
+  req("ar.ada.w", wt, (int64_t)n_ada * c.cond_dim); req("ar.ada.b", DT_F32, n_ada);
+  req("ar.prevkv.w", wt, (int64_t)c.ar_depth * 2 * C * C); req("ar.prevkv.b", DT_F32, c.ar_depth * 2 * C);
+  for (int l = 0; l < c.ar_depth; ++l) {
+    req(S("ar.l%d.qkv.w", l), wt, (int64_t)3 * C * C); req(S("ar.l%d.qkv.b", l), DT_F32, 3 * C);
+    req(S("ar.l%d.head_scale", l), DT_F32, c.ar_heads);
+    req(S("ar.l%d.proj.w", l), wt, (int64_t)C * C); req(S("ar.l%d.proj.b", l), DT_F32, C);
+    req(S("ar.l%d.ff1.w", l), wt, (int64_t)4 * C * C); req(S("ar.l%d.ff1.b", l), DT_F32, 4 * C);
+    req(S("ar.l%d.ff2.w", l), wt, (int64_t)4 * C * C); req(S("ar.l%d.ff2.b", l), DT_F32, C);
+  }
+  req("ar.head.w", wt, (int64_t)2 * c.code_dim * C); req("ar.head.b", DT_F32, 2 * c.code_dim);
+  req("ar.embed.w", DT_F32, (int64_t)C * c.code_dim); req("ar.embed.b", DT_F32, C);
+  req("ar.lvl_pos", DT_F32, (int64_t)L * C); req("ar.prev_lvl_pos", DT_F32, (int64_t)L * C);
+  // VAE
+  for (const char* side : {"dec", "enc"}) {
+    bool dec = side[0] == 'd';
+    req(S("vae.%s.in.w", side), wt, (int64_t)VH * (dec ? c.code_dim : 128)); req(S("vae.%s.in.b", side), DT_F32, VH);
+    for (int l = 0; l < c.vae_depth; ++l) {
+      req(S("vae.%s.l%d.ln_g", side, l), DT_F32, VH); req(S("vae.%s.l%d.ln_b", side, l), DT_F32, VH);
+      req(S("vae.%s.l%d.qkv.w", side, l), wt, (int64_t)3 * VH * VH);
+      req(S("vae.%s.l%d.out.w", side, l), wt, (int64_t)VH * VH); req(S("vae.%s.l%d.out.b", side, l), DT_F32, VH);
+      req(S("vae.%s.l%d.ff1.w", side, l), wt, (int64_t)(VH * 3 / 2) * VH); req(S("vae.%s.l%d.ff1.b", side, l), DT_F32, VH * 3 / 2);
+      req(S("vae.%s.l%d.ff2.w", side, l), wt, (int64_t)VH * (VH * 3 / 2)); req(S("vae.%s.l%d.ff2.b", side, l), DT_F32, VH);
+    }
+    req(S("vae.%s.out.w", side), wt, (int64_t)(dec ? c.motion_dim : c.code_dim) * VH);
+    req(S("vae.%s.out.b", side), DT_F32, dec ? c.motion_dim : c.code_dim);
+  }
+  req("vae.dec_pos", DT_F32, (int64_t)2 * T * c.code_dim); req("vae.enc_pos", DT_F32, (int64_t)T * c.motion_dim);
+  req("vae.mean", DT_F32, c.motion_dim); req("vae.std", DT_F32, c.motion_dim);
+  // style encoder (always fp32)
+  const int SD = c.style_dim;
+  req("style.mean", DT_F32, c.motion_dim); req("style.std", DT_F32, c.motion_dim);
+  req("style.zero_pos", DT_F32, (int64_t)c.style_len * c.motion_dim);
+  req("style.proj.w", DT_F32, (int64_t)SD * 112); req("style.proj.b", DT_F32, SD);
+  for (int l = 0; l < c.style_layers; ++l) {
+    req(S("style.l%d.qkv.w", l), DT_F32, (int64_t)3 * SD * SD); req(S("style.l%d.qkv.b", l), DT_F32, 3 * SD);
+    req(S("style.l%d.out.w", l), DT_F32, (int64_t)SD * SD); req(S("style.l%d.out.b", l), DT_F32, SD);
+    req(S("style.l%d.ln1_g", l), DT_F32, SD); req(S("style.l%d.ln1_b", l), DT_F32, SD);
+    req(S("style.l%d.ff1.w", l), DT_F32, (int64_t)c.style_ffn * SD); req(S("style.l%d.ff1.b", l), DT_F32, c.style_ffn);
+    req(S("style.l%d.ff2.w", l), DT_F32, (int64_t)SD * c.style_ffn); req(S("style.l%d.ff2.b", l), DT_F32, SD);
+    req(S("style.l%d.ln2_g", l), DT_F32, SD); req(S("style.l%d.ln2_b", l), DT_F32, SD);
+  }
+  req("style.embed.w", DT_F32, (int64_t)C * SD); req("style.embed.b", DT_F32, C);
+  req("style.null", DT_F32, C);
+  // operator tables
+  for (const char* n : {"tb.up_i0", "tb.up_i1", "tb.pool_start", "tb.pool_end"}) req(n, 2, (int64_t)c.n_levels * T);
+  req("tb.up_w1", DT_F32, (int64_t)c.n_levels * T);
+  for (const Need& n : need) {
+    const Tensor* t = find(n.name);
+    if (!t) { set_last_error("finalize: missing tensor '%s'", n.name.c_str()); return AT_EMISSING; }
+    if (t->dt != n.dt || t->numel != n.numel) {
+      set_last_error("finalize: tensor '%s' has dtype %d numel %lld, expected dtype %d numel %lld", n.name.c_str(), t->dt,
+                     (long long)t->numel, n.dt, (long long)n.numel);
+      return AT_EINVAL;
+    }
+  }
+  tb.n_levels = c.n_levels; tb.T = T; tb.L = L;
+  int cum = 0;
+  for (int i = 0; i < 8; ++i) { tb.pn[i] = 0; tb.cum[i] = 0; }
+  for (int i = 0; i < c.n_levels; ++i) { tb.pn[i] = c.patch_nums[i]; cum += c.patch_nums[i]; tb.cum[i] = cum; }
+  tb.up_i0 = get<int>("tb.up_i0"); tb.up_i1 = get<int>("tb.up_i1"); tb.up_w1 = get<float>("tb.up_w1");
+  tb.pool_start = get<int>("tb.pool_start"); tb.pool_end = get<int>("tb.pool_end");
+  finalized = true;
+  return AT_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+int Engine::ws_reserve(size_t bytes, cudaStream_t st) {
+  ws_off = 0;
+  if (bytes <= ws_cap) return AT_OK;
+  AT_CUDA(cudaStreamSynchronize(st));
+  if (ws) { AT_CUDA(cudaFree(ws)); ws = nullptr; ws_cap = 0; }
+  cudaError_t e = cudaMalloc((void**)&ws, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("workspace: cudaMalloc(%zu MiB) failed: %s", bytes >> 20, cudaGetErrorString(e));
+    return AT_ENOMEM;
+  }
+  ws_cap = bytes;
+  return AT_OK;
+}
+
+void* Engine::ws_alloc(size_t bytes) {
+  size_t off = (ws_off + 255) & ~(size_t)255;
+  if (off + bytes > ws_cap) { set_last_error("workspace overflow: need %zu at %zu of %zu", bytes, off, ws_cap); return nullptr; }
+  ws_off = off + bytes;
+  return ws + off;
+}
+#define WS(var, type, bytes)                              \
+  type var = (type)ws_alloc(bytes);                       \
+  if (!var) return AT_ENOMEM
+
+int Engine::gemm(const GemmArgs& g, cudaStream_t st) const {
+  return cfg.precision == 0 ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
+}
+
+// ------------------------------------------------------------------ wav2vec2
+size_t Engine::audio_ws_per_chunk() const {
+  const size_t s = dt_size(act_dt());
+  const size_t CD = cfg.w2v_conv_dim, H = cfg.w2v_hidden;
+  size_t bufA = std::max((size_t)conv_len[0] * CD, (size_t)n_audio_frames * std::max((size_t)cfg.w2v_ffn, 3 * H)) * s;
+  size_t bufB = std::max((size_t)conv_len[1] * CD, (size_t)n_audio_frames * H) * s;
+  size_t pre = (size_t)conv_len[1] * CD * 4;
+  size_t h = (size_t)n_audio_frames * H * 4;
+  return bufA + bufB + pre + 2 * h + 4096;
+}
+
+int Engine::audio_encode(const float* audio, int n_chunks, float* cond, cudaStream_t st) {
+  AT_REQUIRE(finalized, "engine not finalized");
+  if (n_chunks <= 0) return AT_OK;
+  size_t per = audio_ws_per_chunk();
+  int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_chunks, ws_limit / per));
+  AT_TRY(ws_reserve((size_t)sub * per + (1 << 20), st));
+  for (int c0 = 0; c0 < n_chunks; c0 += sub) {
+    int n = std::min(sub, n_chunks - c0);
+    ws_reset();
+    AT_TRY(audio_encode_sub(audio + (int64_t)c0 * cfg.chunk_samples, n, cond + (int64_t)c0 * L * cfg.w2v_hidden, st));
+  }
+  return AT_OK;
+}
+
+int Engine::audio_encode_sub(const float* audio, int n, float* cond, cudaStream_t st) {
+  const EngineConfig& c = cfg;
+  const int adt = act_dt();
+  const size_t s = dt_size(adt);
+  const int CD = c.w2v_conv_dim, H = c.w2v_hidden, F = n_audio_frames, M = n * F;
+  WS(stats, float2*, (size_t)n * sizeof(float2));
+  WS(bufA, char*, (size_t)n * std::max((size_t)conv_len[0] * CD, (size_t)F * std::max((size_t)c.w2v_ffn, (size_t)3 * H)) * s);
+  WS(bufB, char*, (size_t)n * std::max((size_t)conv_len[1] * CD, (size_t)F * H) * s);
+  WS(pre, float*, (size_t)n * conv_len[1] * CD * 4);
+  WS(h, float*, (size_t)M * H * 4);
+  WS(h2, float*, (size_t)M * H * 4);
+
+  AT_TRY(launch_audio_stats(audio, n, c.chunk_samples, stats, st));
+  AT_TRY(launch_conv0_ln_gelu(audio, stats, get<float>("w2v.conv0.w"), get<float>("w2v.conv0.b"), get<float>("w2v.conv0.ln_g"),
+                              get<float>("w2v.conv0.ln_b"), bufA, adt, n, c.chunk_samples, conv_len[0], c.w2v_conv_kernel[0],
+                              c.w2v_conv_stride[0], c.w2v_ln_eps, st));
+  char* in = bufA; char* out = bufB;
+  for (int i = 1; i < c.w2v_n_conv; ++i) {
+    // implicit GEMM: row t of the A operand is the contiguous window in[t*stride : t*stride + k][:] of the
+    // channels-last input (overlapping rows, row stride = stride*512)
+    GemmArgs g = gemm_args();
+    g.A = in; g.a_map = batched_rows(conv_len[i], (int64_t)conv_len[i - 1] * CD, (int64_t)c.w2v_conv_stride[i] * CD);
+    g.W = getw(S("w2v.conv%d.w", i)); g.ldw = (int64_t)c.w2v_conv_kernel[i] * CD;
+    g.M = n * conv_len[i]; g.N = CD; g.K = c.w2v_conv_kernel[i] * CD;
+    g.bias = get<float>(S("w2v.conv%d.b", i));
+    g.out32 = pre; g.c_map = plain_rows(CD);
+    AT_TRY(gemm(g, st));
+    bool last = (i == c.w2v_n_conv - 1);
+    // the last conv layer's LN+GELU output feeds another LayerNorm -> keep it fp32 (staged in h)
+    AT_TRY(launch_layernorm(pre, CD, last ? (void*)h : (void*)out, last ? DT_F32 : adt, CD, get<float>(S("w2v.conv%d.ln_g", i)),
+                            get<float>(S("w2v.conv%d.ln_b", i)), g.M, CD, c.w2v_ln_eps, ACT_GELU_ERF, st));
+    std::swap(in, out);
+  }
+  // feature projection: LN(512) -> Linear 512 -> 1024   (modeling_wav2vec2.py:422-434)
+  AT_TRY(launch_layernorm(h, CD, bufB, adt, CD, get<float>("w2v.proj.ln_g"), get<float>("w2v.proj.ln_b"), M, CD, c.w2v_ln_eps,
+                          ACT_NONE, st));
+  {
+    GemmArgs g = gemm_args();
+    g.A = bufB; g.a_map = plain_rows(CD); g.W = getw("w2v.proj.w"); g.ldw = CD; g.M = M; g.N = H; g.K = CD;
+    g.bias = get<float>("w2v.proj.b"); g.out32 = h; g.c_map = plain_rows(H);
+    if (adt != DT_F32) { g.out_act = bufA; g.out_act_dt = adt; }
+    AT_TRY(gemm(g, st));
+  }
+  // positional conv embedding: grouped conv k=128 pad 64 (last output dropped) + GELU + residual (:360-368,764-765)
+  {
+    const int G = c.w2v_pos_groups, gw = H / G;
+    GemmArgs g = gemm_args();
+    g.A = (adt == DT_F32) ? (const void*)h : (const void*)bufA;
+    g.a_map = batched_rows(F, (int64_t)F * H, H);
+    g.tap_w = gw; g.tap_pad = c.w2v_pos_kernel / 2;
+    g.W = getw("w2v.pos.w"); g.ldw = (int64_t)c.w2v_pos_kernel * gw;
+    g.M = M; g.N = gw; g.K = c.w2v_pos_kernel * gw;
+    g.groups = G; g.a_gs = gw; g.w_gs = (int64_t)gw * c.w2v_pos_kernel * gw; g.c_gs = gw; g.bias_gs = gw;
+    g.bias = get<float>("w2v.pos.b"); g.act = ACT_GELU_ERF;
+    g.resid = h; g.resid_map = plain_rows(H); g.out32 = h2; g.c_map = plain_rows(H);
+    AT_TRY(gemm(g, st));
+    std::swap(h, h2);
+  }
+  const float att_scale = 1.0f / sqrtf((float)(H / c.w2v_heads));
+  for (int l = 0; l < c.w2v_layers; ++l) {
+    AT_TRY(launch_layernorm(h, H, bufB, adt, H, get<float>(S("w2v.l%d.ln1_g", l)), get<float>(S("w2v.l%d.ln1_b", l)), M, H,
+                            c.w2v_ln_eps, ACT_NONE, st));
+    GemmArgs g = gemm_args();
+    g.A = bufB; g.a_map = plain_rows(H); g.W = getw(S("w2v.l%d.qkv.w", l)); g.ldw = H; g.M = M; g.N = 3 * H; g.K = H;
+    g.bias = get<float>(S("w2v.l%d.qkv.b", l)); g.out_act = bufA; g.out_act_dt = adt; g.c_map = plain_rows(3 * H);
+    AT_TRY(gemm(g, st));
+    AttnArgs a;
+    a.q = bufA; a.k = bufA + (size_t)H * s; a.v = bufA + (size_t)2 * H * s; a.out = bufB; a.dt = adt;
+    a.n_seq = n; a.n_heads = c.w2v_heads; a.head_dim = H / c.w2v_heads; a.lq = F; a.lk = F;
+    a.q_ss = a.k_ss = a.v_ss = (int64_t)F * 3 * H; a.q_rs = a.k_rs = a.v_rs = 3 * H;
+    a.o_ss = (int64_t)F * H; a.o_rs = H; a.scale = att_scale; a.split = 0;
+    AT_TRY(launch_attention(a, st));
+    g = gemm_args();
+    g.A = bufB; g.a_map = plain_rows(H); g.W = getw(S("w2v.l%d.out.w", l)); g.ldw = H; g.M = M; g.N = H; g.K = H;
+    g.bias = get<float>(S("w2v.l%d.out.b", l)); g.resid = h; g.resid_map = plain_rows(H); g.out32 = h; g.c_map = plain_rows(H);
+    AT_TRY(gemm(g, st));
+    AT_TRY(launch_layernorm(h, H, bufB, adt, H, get<float>(S("w2v.l%d.ln2_g", l)), get<float>(S("w2v.l%d.ln2_b", l)), M, H,
+                            c.w2v_ln_eps, ACT_NONE, st));
+    g = gemm_args();
+    g.A = bufB; g.a_map = plain_rows(H); g.W = getw(S("w2v.l%d.ff1.w", l)); g.ldw = H; g.M = M; g.N = c.w2v_ffn; g.K = H;
+    g.bias = get<float>(S("w2v.l%d.ff1.b", l)); g.act = ACT_GELU_ERF; g.out_act = bufA; g.out_act_dt = adt;
+    g.c_map = plain_rows(c.w2v_ffn);
+    AT_TRY(gemm(g, st));
+    g = gemm_args();
+    g.A = bufA; g.a_map = plain_rows(c.w2v_ffn); g.W = getw(S("w2v.l%d.ff2.w", l)); g.ldw = c.w2v_ffn; g.M = M; g.N = H;
+    g.K = c.w2v_ffn; g.bias = get<float>(S("w2v.l%d.ff2.b", l)); g.resid = h; g.resid_map = plain_rows(H); g.out32 = h;
+    g.c_map = plain_rows(H);
+    AT_TRY(gemm(g, st));
+  }
+  AT_TRY(launch_layernorm(h, H, h2, DT_F32, H, get<float>("w2v.enc_ln_g"), get<float>("w2v.enc_ln_b"), M, H, c.w2v_ln_eps,
+                          ACT_NONE, st));
+  AT_TRY(launch_audio_pool(h2, cond, n, F, H, c.patch_nums, c.n_levels, st));
+  return AT_OK;
+}
+
+// ------------------------------------------------------------------ style encoder (fp32, once per clip)
+int Engine::style_encode(const float* style_motion, int n, float* style_out, cudaStream_t st) {
+  AT_REQUIRE(finalized, "engine not finalized");
+  if (n <= 0) return AT_OK;
+  const EngineConfig& c = cfg;
+  const int SD = c.style_dim, SL = c.style_len, M = n * SL, KP = 112;
+  AT_TRY(ws_reserve((size_t)M * (KP + SD * 2 + 3 * SD + SD + c.style_ffn) * 4 + (size_t)n * SD * 4 + (1 << 16), st));
+  WS(xin, float*, (size_t)M * KP * 4);
+  WS(x, float*, (size_t)M * SD * 4);
+  WS(t, float*, (size_t)M * SD * 4);
+  WS(qkv, float*, (size_t)M * 3 * SD * 4);
+  WS(o, float*, (size_t)M * SD * 4);
+  WS(f, float*, (size_t)M * c.style_ffn * 4);
+  WS(pooled, float*, (size_t)n * SD * 4);
+  AT_TRY(launch_motion_norm_pos(style_motion, get<float>("style.mean"), get<float>("style.std"), get<float>("style.zero_pos"), xin,
+                                DT_F32, n, SL, c.motion_dim, KP, st));
+  GemmArgs g = gemm_args();
+  g.A = xin; g.a_map = plain_rows(KP); g.W = getw("style.proj.w"); g.ldw = KP; g.M = M; g.N = SD; g.K = KP;
+  g.bias = get<float>("style.proj.b"); g.out32 = x; g.c_map = plain_rows(SD);       // bias already holds + pe[style_len]
+  AT_TRY(launch_gemm_simt(g, st));
+  for (int l = 0; l < c.style_layers; ++l) {
+    g = gemm_args();
+    g.A = x; g.a_map = plain_rows(SD); g.W = getw(S("style.l%d.qkv.w", l)); g.ldw = SD; g.M = M; g.N = 3 * SD; g.K = SD;
+    g.bias = get<float>(S("style.l%d.qkv.b", l)); g.out32 = qkv; g.c_map = plain_rows(3 * SD);
+    AT_TRY(launch_gemm_simt(g, st));
+    AttnArgs a;
+    a.q = qkv; a.k = qkv + SD; a.v = qkv + 2 * SD; a.out = o; a.dt = DT_F32; a.n_seq = n; a.n_heads = c.style_heads;
+    a.head_dim = SD / c.style_heads; a.lq = SL; a.lk = SL; a.q_ss = a.k_ss = a.v_ss = (int64_t)SL * 3 * SD;
+    a.q_rs = a.k_rs = a.v_rs = 3 * SD; a.o_ss = (int64_t)SL * SD; a.o_rs = SD;
+    a.scale = 1.0f / sqrtf((float)a.head_dim); a.split = 0;
+    AT_TRY(launch_attention(a, st));
+    g = gemm_args();
+    g.A = o; g.a_map = plain_rows(SD); g.W = getw(S("style.l%d.out.w", l)); g.ldw = SD; g.M = M; g.N = SD; g.K = SD;
+    g.bias = get<float>(S("style.l%d.out.b", l)); g.resid = x; g.resid_map = plain_rows(SD); g.out32 = t; g.c_map = plain_rows(SD);
+    AT_TRY(launch_gemm_simt(g, st));
+    AT_TRY(launch_layernorm(t, SD, x, DT_F32, SD, get<float>(S("style.l%d.ln1_g", l)), get<float>(S("style.l%d.ln1_b", l)), M, SD,
+                            1e-5f, ACT_NONE, st));                                        // post-norm
+    g = gemm_args();
+    g.A = x; g.a_map = plain_rows(SD); g.W = getw(S("style.l%d.ff1.w", l)); g.ldw = SD; g.M = M; g.N = c.style_ffn; g.K = SD;
+    g.bias = get<float>(S("style.l%d.ff1.b", l)); g.act = ACT_GELU_ERF; g.out32 = f; g.c_map = plain_rows(c.style_ffn);
+    AT_TRY(launch_gemm_simt(g, st));
+    g = gemm_args();
+    g.A = f; g.a_map = plain_rows(c.style_ffn); g.W = getw(S("style.l%d.ff2.w", l)); g.ldw = c.style_ffn; g.M = M; g.N = SD;
+    g.K = c.style_ffn; g.bias = get<float>(S("style.l%d.ff2.b", l)); g.resid = x; g.resid_map = plain_rows(SD); g.out32 = t;
+    g.c_map = plain_rows(SD);
+    AT_TRY(launch_gemm_simt(g, st));
+    AT_TRY(launch_layernorm(t, SD, x, DT_F32, SD, get<float>(S("style.l%d.ln2_g", l)), get<float>(S("style.l%d.ln2_b", l)), M, SD,
+                            1e-5f, ACT_NONE, st));
+  }
+  int one = 1;
+  AT_TRY(launch_audio_pool(x, pooled, n, SL, SD, &one, 1, st));                        // mean over time
+  g = gemm_args();
+  g.A = pooled; g.a_map = plain_rows(SD); g.W = getw("style.embed.w"); g.ldw = SD; g.M = n; g.N = c.embed_dim; g.K = SD;
+  g.bias = get<float>("style.embed.b"); g.out32 = style_out; g.c_map = plain_rows(c.embed_dim);   // 1.1*W, 1.1*b - 0.1*null folded
+  AT_TRY(launch_gemm_simt(g, st));
+  return AT_OK;
+}
+
+// ------------------------------------------------------------------ VAE transformer stack (bitwise_vae.py:128-215)
+// x: fp32 residual stream [n*rows, 512]; xa: act copy of x (bf16 mode) or null (fp32 mode: x itself is the operand)
+int Engine::vae_stack(const char* side, int n, int rows, int split, float* x, void* xa, cudaStream_t st) {
+  const EngineConfig& c = cfg;
+  const int adt = act_dt(), VH = c.vae_hidden, M = n * rows, FF = VH * 3 / 2;
+  const size_t s = dt_size(adt);
+  WS(nv, char*, (size_t)M * VH * s);
+  WS(qkv, char*, (size_t)M * 3 * VH * s);
+  WS(f, char*, (size_t)M * FF * s);
+  const void* x_op = (adt == DT_F32) ? (const void*)x : (const void*)xa;
+  for (int l = 0; l < c.vae_depth; ++l) {
+    AT_TRY(launch_layernorm(x, VH, nv, adt, VH, get<float>(S("vae.%s.l%d.ln_g", side, l)), get<float>(S("vae.%s.l%d.ln_b", side, l)),
+                            M, VH, 1e-5f, ACT_NONE, st));
+    GemmArgs g = gemm_args();
+    g.A = nv; g.a_map = plain_rows(VH); g.W = getw(S("vae.%s.l%d.qkv.w", side, l)); g.ldw = VH; g.M = M; g.N = 3 * VH; g.K = VH;
+    g.out_act = qkv; g.out_act_dt = adt; g.c_map = plain_rows(3 * VH);
+    AT_TRY(gemm(g, st));
+    AttnArgs a;     // to_qkv layout (qkv, head, d): q | k | v blocks of 512 columns (quirk 3)
+    a.q = qkv; a.k = qkv + (size_t)VH * s; a.v = qkv + (size_t)2 * VH * s; a.out = nv; a.dt = adt;
+    a.n_seq = n; a.n_heads = c.vae_heads; a.head_dim = 64; a.lq = rows; a.lk = rows;
+    a.q_ss = a.k_ss = a.v_ss = (int64_t)rows * 3 * VH; a.q_rs = a.k_rs = a.v_rs = 3 * VH; a.o_ss = (int64_t)rows * VH; a.o_rs = VH;
+    a.scale = 1.0f / sqrtf((float)VH);            // quirk 2: hidden_dim ** -0.5
+    a.split = split;
+    AT_TRY(launch_attention(a, st));
+    g = gemm_args();
+    g.A = nv; g.a_map = plain_rows(VH); g.W = getw(S("vae.%s.l%d.out.w", side, l)); g.ldw = VH; g.M = M; g.N = VH; g.K = VH;
+    g.bias = get<float>(S("vae.%s.l%d.out.b", side, l)); g.resid = x; g.resid_map = plain_rows(VH); g.out32 = x; g.c_map = plain_rows(VH);
+    if (adt != DT_F32) { g.out_act = xa; g.out_act_dt = adt; }
+    AT_TRY(gemm(g, st));
+    g = gemm_args();      // MLP on the un-normalised stream
+    g.A = x_op; g.a_map = plain_rows(VH); g.W = getw(S("vae.%s.l%d.ff1.w", side, l)); g.ldw = VH; g.M = M; g.N = FF; g.K = VH;
+    g.bias = get<float>(S("vae.%s.l%d.ff1.b", side, l)); g.act = ACT_GELU_TANH; g.out_act = f; g.out_act_dt = adt; g.c_map = plain_rows(FF);
+    AT_TRY(gemm(g, st));
+    g = gemm_args();
+    g.A = f; g.a_map = plain_rows(FF); g.W = getw(S("vae.%s.l%d.ff2.w", side, l)); g.ldw = FF; g.M = M; g.N = VH; g.K = FF;
+    g.bias = get<float>(S("vae.%s.l%d.ff2.b", side, l)); g.resid = x; g.resid_map = plain_rows(VH); g.out32 = x; g.c_map = plain_rows(VH);
+    if (adt != DT_F32) { g.out_act = xa; g.out_act_dt = adt; }
+    AT_TRY(gemm(g, st));
+  }
+  return AT_OK;
+}
+
+int Engine::vae_decode(const uint32_t* prev_words, const uint32_t* words, int n, float* motion, cudaStream_t st) {
+  const EngineConfig& c = cfg;
+  const int adt = act_dt(), VH = c.vae_hidden, rows = 2 * T, M = n * rows;
+  const size_t s = dt_size(adt);
+  size_t mark = ws_off;
+  WS(z, char*, (size_t)M * c.code_dim * s);
+  WS(x, float*, (size_t)M * VH * 4);
+  char* xa = nullptr;
+  if (adt != DT_F32) { xa = (char*)ws_alloc((size_t)M * VH * s); if (!xa) return AT_ENOMEM; }
+  AT_TRY(launch_bits_latent(tb, prev_words, L, get<float>("vae.dec_pos"), z, adt, n, 0, st));
+  AT_TRY(launch_bits_latent(tb, words, L, get<float>("vae.dec_pos"), z, adt, n, 1, st));
+  GemmArgs g = gemm_args();
+  g.A = z; g.a_map = plain_rows(c.code_dim); g.W = getw("vae.dec.in.w"); g.ldw = c.code_dim; g.M = M; g.N = VH; g.K = c.code_dim;
+  g.bias = get<float>("vae.dec.in.b"); g.act = ACT_LEAKY02; g.out32 = x; g.c_map = plain_rows(VH);
+  if (adt != DT_F32) { g.out_act = xa; g.out_act_dt = adt; }
+  AT_TRY(gemm(g, st));
+  AT_TRY(vae_stack("dec", n, rows, T, x, xa, st));
+  // out_mapping on the new half only (rows T..2T of each clip); motion_std / motion_mean folded into W, b
+  g = gemm_args();
+  const char* src = (adt == DT_F32) ? (const char*)x : (const char*)xa;
+  g.A = src + (size_t)T * VH * s; g.a_map = batched_rows(T, (int64_t)rows * VH, VH);
+  g.W = getw("vae.dec.out.w"); g.ldw = VH; g.M = n * T; g.N = c.motion_dim; g.K = VH;
+  g.bias = get<float>("vae.dec.out.b"); g.out32 = motion; g.c_map = plain_rows(c.motion_dim);
+  AT_TRY(gemm(g, st));
+  ws_off = mark;
+  return AT_OK;
+}
+
+int Engine::vae_encode_bits(const float* motion, int n, uint32_t* words_out, float* enc_out_opt, cudaStream_t st) {
+  const EngineConfig& c = cfg;
+  const int adt = act_dt(), VH = c.vae_hidden, M = n * T, KP = 128;
+  const size_t s = dt_size(adt);
+  size_t mark = ws_off;
+  WS(xin, char*, (size_t)M * KP * s);
+  WS(x, float*, (size_t)M * VH * 4);
+  char* xa = nullptr;
+  if (adt != DT_F32) { xa = (char*)ws_alloc((size_t)M * VH * s); if (!xa) return AT_ENOMEM; }
+  float* enc = enc_out_opt;
+  if (!enc) { enc = (float*)ws_alloc((size_t)M * c.code_dim * 4); if (!enc) return AT_ENOMEM; }
+  AT_TRY(launch_motion_norm_pos(motion, get<float>("vae.mean"), get<float>("vae.std"), get<float>("vae.enc_pos"), xin, adt, n, T,
+                                c.motion_dim, KP, st));
+  GemmArgs g = gemm_args();
+  g.A = xin; g.a_map = plain_rows(KP); g.W = getw("vae.enc.in.w"); g.ldw = KP; g.M = M; g.N = VH; g.K = KP;
+  g.bias = get<float>("vae.enc.in.b"); g.act = ACT_LEAKY02; g.out32 = x; g.c_map = plain_rows(VH);
+  if (adt != DT_F32) { g.out_act = xa; g.out_act_dt = adt; }
+  AT_TRY(gemm(g, st));
+  AT_TRY(vae_stack("enc", n, T, 0, x, xa, st));
+  g = gemm_args();
+  g.A = (adt == DT_F32) ? (const void*)x : (const void*)xa; g.a_map = plain_rows(VH);
+  g.W = getw("vae.enc.out.w"); g.ldw = VH; g.M = M; g.N = c.code_dim; g.K = VH;
+  g.bias = get<float>("vae.enc.out.b"); g.out32 = enc; g.c_map = plain_rows(c.code_dim);
+  AT_TRY(gemm(g, st));
+  AT_TRY(launch_bsq_quantize(tb, enc, words_out, L, n, st));
+  ws_off = mark;
+  return AT_OK;
+}
+
+// ------------------------------------------------------------------ one 100-frame chunk of the AR recurrence
+int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* style, uint32_t* prev_words, float* motion_out,
+                     uint32_t* words_out, float* logits_out, const uint32_t* forced_words, float* enc_out, cudaStream_t st) {
+  AT_REQUIRE(finalized, "engine not finalized");
+  if (B <= 0) return AT_OK;
+  const EngineConfig& c = cfg;
+  const int adt = act_dt(), C = c.embed_dim, D = c.cond_dim, NL = c.ar_depth;
+  const size_t s = dt_size(adt);
+  const int n_ada = NL * 6 * C + 2 * C, P = L, KV = P + L, Tm = T;
+  const int64_t BL = (int64_t)B * L;
+  size_t need = (size_t)BL * D * s + (size_t)BL * n_ada * s + (size_t)BL * C * s + (size_t)BL * NL * 2 * C * s +
+                2 * (size_t)NL * B * KV * C * s + (size_t)B * Tm * C * (4 + 3 * s) + (size_t)B * Tm * 4 * C * s +
+                (size_t)BL * 2 * c.code_dim * 4 + (size_t)BL * 4 +
+                (size_t)B * 2 * Tm * (c.code_dim * s + c.vae_hidden * (4 + s) + c.vae_hidden * s * 4 + c.vae_hidden * s * 3 / 2) +
+                (size_t)B * Tm * (128 * s + c.code_dim * 4) + (4 << 20);
+  AT_TRY(ws_reserve(need, st));
+  WS(scond, char*, (size_t)BL * D * s);
+  WS(ada, char*, (size_t)BL * n_ada * s);
+  WS(prev_tok, char*, (size_t)BL * C * s);
+  WS(kvtmp, char*, (size_t)BL * NL * 2 * C * s);            // prev K|V of all layers; later reused as per-step qkv
+  WS(kcache, char*, (size_t)NL * B * KV * C * s);
+  WS(vcache, char*, (size_t)NL * B * KV * C * s);
+  WS(x, float*, (size_t)B * Tm * C * 4);
+  WS(u, char*, (size_t)B * Tm * C * s);
+  WS(qbuf, char*, (size_t)B * Tm * C * s);
+  WS(o, char*, (size_t)B * Tm * C * s);
+  WS(f, char*, (size_t)B * Tm * 4 * C * s);
+  float* logits = logits_out;
+  if (!logits) { logits = (float*)ws_alloc((size_t)BL * 2 * c.code_dim * 4); if (!logits) return AT_ENOMEM; }
+  uint32_t* words = words_out;
+  if (!words) { words = (uint32_t*)ws_alloc((size_t)BL * 4); if (!words) return AT_ENOMEM; }
+
+  // AdaLN parameters of every block + head for all 181 tokens, once per chunk (audio-only)
+  AT_TRY(launch_act_cast(cond, batched_rows(L, cond_cs, D), scond, adt, (int)BL, D, ACT_SILU, st));
+  GemmArgs g = gemm_args();
+  g.A = scond; g.a_map = plain_rows(D); g.W = getw("ar.ada.w"); g.ldw = D; g.M = (int)BL; g.N = n_ada; g.K = D;
+  g.bias = get<float>("ar.ada.b"); g.out_act = ada; g.out_act_dt = adt; g.c_map = plain_rows(n_ada);
+  AT_TRY(gemm(g, st));
+  // previous-chunk tokens (+ prev_lvl_pos) and their K/V for all blocks (same raw input for every block, quirk 8)
+  AT_TRY(launch_bits_tokens(tb, prev_words, L, style, get<float>("ar.embed.w"), get<float>("ar.embed.b"), get<float>("ar.prev_lvl_pos"),
+                            prev_tok, adt, B, 0, c.n_levels - 1, C, st));
+  g = gemm_args();
+  g.A = prev_tok; g.a_map = plain_rows(C); g.W = getw("ar.prevkv.w"); g.ldw = C; g.M = (int)BL; g.N = NL * 2 * C; g.K = C;
+  g.bias = get<float>("ar.prevkv.b"); g.out_act = kvtmp; g.out_act_dt = adt; g.c_map = plain_rows(NL * 2 * C);
+  AT_TRY(gemm(g, st));
+  for (int l = 0; l < NL; ++l)
+    AT_TRY(launch_qkv_norm_scatter(kvtmp + (size_t)l * 2 * C * s, adt, (int64_t)NL * 2 * C, 0, nullptr, nullptr,
+                                   kcache + (size_t)l * B * KV * C * s, vcache + (size_t)l * B * KV * C * s,
+                                   batched_rows(P, (int64_t)KV * C, C), (int)BL, c.ar_heads, st));
+  for (int p = 0; p < c.n_levels; ++p) {
+    const int n_new = c.patch_nums[p], off = p ? tb.cum[p - 1] : 0, M = B * n_new;
+    const RowMap ada_map = batched_rows(n_new, (int64_t)L * n_ada, n_ada);
+    const char* ada_p = ada + (size_t)off * n_ada * s;
+    const uint32_t* src_words = forced_words ? forced_words : words;
+    AT_TRY(launch_bits_tokens(tb, src_words, L, style, get<float>("ar.embed.w"), get<float>("ar.embed.b"), get<float>("ar.lvl_pos"), x,
+                              DT_F32, B, p, p, C, st));
+    for (int l = 0; l < NL; ++l) {
+      const char* ada_l = ada_p + (size_t)l * 6 * C * s;     // chunk order: g1, g2, s1, s2, b1, b2 (quirk 9)
+      AT_TRY(launch_adaln_modulate(x, ada_l, adt, ada_map, 2 * C, 4 * C, u, adt, M, C, 1e-6f, st));
+      g = gemm_args();
+      g.A = u; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.qkv.w", l)); g.ldw = C; g.M = M; g.N = 3 * C; g.K = C;
+      g.bias = get<float>(S("ar.l%d.qkv.b", l)); g.out_act = kvtmp; g.out_act_dt = adt; g.c_map = plain_rows(3 * C);
+      AT_TRY(gemm(g, st));
+      char* kc = kcache + (size_t)l * B * KV * C * s; char* vc = vcache + (size_t)l * B * KV * C * s;
+      AT_TRY(launch_qkv_norm_scatter(kvtmp, adt, 3 * C, 1, get<float>(S("ar.l%d.head_scale", l)), qbuf, kc + (size_t)(P + off) * C * s,
+                                     vc + (size_t)(P + off) * C * s, batched_rows(n_new, (int64_t)KV * C, C), M, c.ar_heads, st));
+      AttnArgs a;
+      a.q = qbuf; a.k = kc; a.v = vc; a.out = o; a.dt = adt; a.n_seq = B; a.n_heads = c.ar_heads; a.head_dim = 64;
+      a.lq = n_new; a.lk = P + off + n_new;          // prev chunk + every current token of scale <= p
+      a.q_ss = (int64_t)n_new * C; a.q_rs = C; a.k_ss = a.v_ss = (int64_t)KV * C; a.k_rs = a.v_rs = C;
+      a.o_ss = (int64_t)n_new * C; a.o_rs = C; a.scale = 1.0f; a.split = 0;
+      AT_TRY(launch_attention(a, st));
+      g = gemm_args();
+      g.A = o; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.proj.w", l)); g.ldw = C; g.M = M; g.N = C; g.K = C;
+      g.bias = get<float>(S("ar.l%d.proj.b", l)); g.gate = ada_l; g.gate_dt = adt; g.gate_map = ada_map;       // gamma1
+      g.resid = x; g.resid_map = plain_rows(C); g.out32 = x; g.c_map = plain_rows(C);
+      AT_TRY(gemm(g, st));
+      AT_TRY(launch_adaln_modulate(x, ada_l, adt, ada_map, 3 * C, 5 * C, u, adt, M, C, 1e-6f, st));
+      g = gemm_args();
+      g.A = u; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.ff1.w", l)); g.ldw = C; g.M = M; g.N = 4 * C; g.K = C;
+      g.bias = get<float>(S("ar.l%d.ff1.b", l)); g.act = ACT_GELU_TANH; g.out_act = f; g.out_act_dt = adt; g.c_map = plain_rows(4 * C);
+      AT_TRY(gemm(g, st));
+      g = gemm_args();
+      g.A = f; g.a_map = plain_rows(4 * C); g.W = getw(S("ar.l%d.ff2.w", l)); g.ldw = 4 * C; g.M = M; g.N = C; g.K = 4 * C;
+      g.bias = get<float>(S("ar.l%d.ff2.b", l)); g.gate = ada_l + (size_t)C * s; g.gate_dt = adt; g.gate_map = ada_map;   // gamma2
+      g.resid = x; g.resid_map = plain_rows(C); g.out32 = x; g.c_map = plain_rows(C);
+      AT_TRY(gemm(g, st));
+    }
+    // head: AdaLN (scale, shift order) -> Linear 768 -> 64 -> pairwise argmax (app/models.py:103-104,145-148)
+    const char* ada_h = ada_p + (size_t)NL * 6 * C * s;
+    AT_TRY(launch_adaln_modulate(x, ada_h, adt, ada_map, 0, C, u, adt, M, C, 1e-6f, st));
+    g = gemm_args();
+    g.A = u; g.a_map = plain_rows(C); g.W = getw("ar.head.w"); g.ldw = C; g.M = M; g.N = 2 * c.code_dim; g.K = C;
+    g.bias = get<float>("ar.head.b"); g.out32 = logits + (size_t)off * 2 * c.code_dim;
+    g.c_map = batched_rows(n_new, (int64_t)L * 2 * c.code_dim, 2 * c.code_dim);
+    AT_TRY(gemm(g, st));
+    AT_TRY(launch_argmax_bits(logits + (size_t)off * 2 * c.code_dim, g.c_map, words + off, batched_rows(n_new, L, 1), M, st));
+  }
+  // VAE decode with the *re-encoded* prev bits (quirk 7), then re-encode the prediction for the next chunk
+  AT_TRY(vae_decode(prev_words, forced_words ? forced_words : words, B, motion_out, st));
+  AT_TRY(vae_encode_bits(motion_out, B, prev_words, enc_out, st));
+  return AT_OK;
+}
+
+}  // namespace artalk

@@ -1,0 +1,128 @@
+// Host-side launchers of every kernel in the library. All launches are asynchronous on `st`.
+// DType: 0 = f32, 1 = bf16 ("act" tensors feeding GEMM A operands are bf16 in bf16 mode).
+#pragma once
+#include "common.cuh"
+
+namespace artalk {
+
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// ---------------- norms.cu ----------------
+// out[r] = act(LN_eps(x[r]) * gamma + beta); gamma/beta may be null (no affine). cols in {128,512,768,1024}.
+int launch_layernorm(const float* x, int64_t x_rs, void* out, int out_dt, int64_t out_rs, const float* gamma,
+                     const float* beta, int rows, int cols, float eps, int act, cudaStream_t st);
+// out[r] = LN_eps(x[r]) * (1 + ada[map(r)][scale_off + c]) + ada[map(r)][shift_off + c]   (app/transformer.py:35,40)
+int launch_adaln_modulate(const float* x, const void* ada, int ada_dt, RowMap ada_map, int scale_off, int shift_off,
+                          void* out, int out_dt, int rows, int cols, float eps, cudaStream_t st);
+// stats[chunk] = (mean, 1/(std_unbiased + 1e-6))   (app/modules/wav2vec.py:23-27)
+int launch_audio_stats(const float* audio, int n_chunks, int n_samples, float2* stats, cudaStream_t st);
+// conv layer 0 (Cin=1,k=10,s=5) on normalised audio + LN(512) + GELU_erf, channels-last output [n, L_out, 512]
+int launch_conv0_ln_gelu(const float* audio, const float2* stats, const float* w_kc, const float* bias,
+                         const float* ln_g, const float* ln_b, void* out, int out_dt, int n_chunks, int n_samples,
+                         int l_out, int kernel, int stride, float eps, cudaStream_t st);
+// adaptive average pooling over time to each patch size, concatenated: [n, Lin, C] -> [n, sum(pn), C] (app/models.py:94-95)
+int launch_audio_pool(const float* x, float* cond, int n, int l_in, int cols, const int* patch_nums, int n_levels,
+                      cudaStream_t st);
+// out[r][c] = act(x[map(r)][c]) cast to out_dt
+int launch_act_cast(const float* x, RowMap x_map, void* out, int out_dt, int rows, int cols, int act, cudaStream_t st);
+
+// ---------------- gemm ----------------
+struct GemmArgs {
+  // C[M,N] = A[M,K] * W[N,K]^T ; A rows addressed through a_map, K contiguous
+  const void* A; RowMap a_map;
+  const void* W; int64_t ldw;          // W row stride (elements)
+  int M, N, K;
+  // tap mode (grouped temporal conv): K = taps*tap_w ; element (r,k): j=k/tap_w, c=k%tap_w ->
+  // A[batch(r)][t(r)+j-tap_pad][c], zero outside [0, a_map.rpb)
+  int tap_w, tap_pad;
+  // groups: blockIdx.z = g ; per-group element offsets
+  int groups; int64_t a_gs, w_gs, c_gs; int bias_gs;
+  const float* bias;                    // [N] or null
+  int act;                              // applied to acc + bias
+  const void* gate; int gate_dt; RowMap gate_map;   // optional per-element multiplier gate[map(r)][c]
+  const float* resid; RowMap resid_map;             // optional fp32 addend (may alias out32)
+  float* out32; void* out_act; int out_act_dt; RowMap c_map;   // either/both outputs, same row map
+};
+static inline GemmArgs gemm_args() {
+  GemmArgs g;
+  g.A = nullptr; g.a_map = plain_rows(0); g.W = nullptr; g.ldw = 0; g.M = g.N = g.K = 0;
+  g.tap_w = 0; g.tap_pad = 0; g.groups = 1; g.a_gs = g.w_gs = g.c_gs = 0; g.bias_gs = 0;
+  g.bias = nullptr; g.act = ACT_NONE; g.gate = nullptr; g.gate_dt = DT_F32; g.gate_map = plain_rows(0);
+  g.resid = nullptr; g.resid_map = plain_rows(0); g.out32 = nullptr; g.out_act = nullptr; g.out_act_dt = DT_F32;
+  g.c_map = plain_rows(0);
+  return g;
+}
+// fp32 CUDA-core GEMM (A and W fp32). gemm_simt.cu
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
+// bf16 tcgen05/TMEM GEMM fed by TMA (A and W bf16). gemm_tc.cu
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+
+// ---------------- attention.cu ----------------
+struct AttnArgs {
+  const void* q; const void* k; const void* v; void* out;   // dtype dt
+  int dt;
+  int n_seq, n_heads, head_dim;      // head_dim in {32, 64}
+  int lq, lk;
+  int64_t q_ss, q_rs;                // sequence stride, row stride (elements); head h at column h*head_dim
+  int64_t k_ss, k_rs, v_ss, v_rs;
+  int64_t o_ss, o_rs;
+  float scale;
+  int split;                          // >0: query rows < split only see keys < split (bitwise_vae.py:67-76)
+};
+int launch_attention(const AttnArgs& a, cudaStream_t st);
+// AR q/k/v post-processing (app/transformer.py:71-74): per-head L2 normalise q (x exp(min(scale_mul, ln100))) and k,
+// q -> qbuf [M, C]; k,v -> cache rows given by kv_map. qkv: [M, 3C] (q | k | v), or [M, 2C] (k | v) when has_q = 0.
+int launch_qkv_norm_scatter(const void* qkv, int dt, int64_t qkv_rs, int has_q, const float* head_scale, void* qbuf,
+                            void* kcache, void* vcache, RowMap kv_map, int rows, int n_heads, cudaStream_t st);
+
+// ---------------- bits.cu ----------------
+struct ScaleOps;   // device tables of the up/down-sampling operators, built by bits_build_tables
+struct BitsTables {
+  int n_levels; int pn[8]; int cum[8]; int T; int L;
+  // linear upsample pn[k] -> T (align_corners = False): for level k and target t: i0, i1, w1
+  const int* up_i0; const int* up_i1; const float* up_w1;     // [n_levels][T]
+  // area pool T -> pn[k]: window [start, end)
+  const int* pool_start; const int* pool_end;                  // [n_levels][T]
+};
+// logits [rows,64] f32 (row map) -> bit j = (l[2j+1] > l[2j]), one packed word per token (app/models.py:104)
+int launch_argmax_bits(const float* logits, RowMap l_map, uint32_t* words, RowMap w_map, int rows, cudaStream_t st);
+// tokens from bits (bitwise_vae.py:264-305 + app/models.py:89,100,107,113): for levels q in [q_lo, q_hi]:
+//   q = 0 : style ; q >= 1 : embed(A_{pn[q]} f_{q-1})      (+ pos[cum_{q-1} + i])
+// written to out rows (clip, row_off + i) with row_off = (cum_{q-1} - cum_{q_lo - 1}).
+int launch_bits_tokens(const BitsTables& tb, const uint32_t* words, int64_t words_cs, const float* style,
+                       const float* embed_w, const float* embed_b, const float* pos, void* out, int out_dt,
+                       int n_clips, int q_lo, int q_hi, int C, cudaStream_t st);
+// decoder latent (bitwise_vae.py:280-288) + dec_pos_embed rows [half*T, half*T+T): out[clip][half*T + t][32]
+int launch_bits_latent(const BitsTables& tb, const uint32_t* words, int64_t words_cs, const float* dec_pos, void* out,
+                       int out_dt, int n_clips, int half, cudaStream_t st);
+// residual multi-scale BSQ (bitwise_vae.py:227-242,316-334): enc_out [n,T,32] f32 -> words [n, L]
+int launch_bsq_quantize(const BitsTables& tb, const float* enc_out, uint32_t* words, int64_t words_cs, int n_clips,
+                        cudaStream_t st);
+// (motion - mean)/std + enc_pos, zero padded to k_pad columns (bitwise_vae.py:88-89)
+int launch_motion_norm_pos(const float* motion, const float* mean, const float* stdv, const float* pos, void* out,
+                           int out_dt, int n_clips, int T, int dim, int k_pad, cudaStream_t st);
+
+// ---------------- flame.cu ----------------
+struct FlameModel {
+  int V, n_shape, n_exp;                  // 5023, 300, 100  (+36 pose-corrective bases)
+  const float* v_template;                // [V*3]
+  const float* dirs;                      // [n_shape + n_exp + 36][V*3]  blend bases, basis-major
+  const float* j_template;                // [5*3]   J_regressor @ v_template
+  const float* j_dirs;                    // [n_shape + n_exp][15]  J_regressor @ shapedirs
+  const float* lbs_weights;               // [V][5]
+  int parents[5];
+  float scale;
+};
+// shape (N,300) [stride 0 allowed for a shared shape row], expr (N,100), pose6 (N,6) -> verts (N,V,3)
+int launch_flame(const FlameModel& fm, const float* shape, int64_t shape_rs, const float* expr, int64_t expr_rs,
+                 const float* pose, int64_t pose_rs, int zero_global, float* coef_ws, float* verts, int n_frames,
+                 cudaStream_t st);
+size_t flame_workspace_floats(const FlameModel& fm, int n_frames);
+
+// ---------------- postproc.cu ----------------
+// Savitzky-Golay (win 5/poly 2; dims 100:103 win 9/poly 3, mode 'interp') + clip + pose/eye zeroing (inference.py:52-56,89-95)
+int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int T_out, int dim, int fix_pose,
+                       int zero_tail, cudaStream_t st);
+
+}  // namespace artalk

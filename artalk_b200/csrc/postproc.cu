@@ -1,0 +1,61 @@
+// Savitzky-Golay smoothing + output post-ops of ARTAvatarInferEngine.inference (inference.py:52-56,89-95) on the device:
+// window 5 / poly 2 on every dim, window 9 / poly 3 on dims 100:103, scipy mode 'interp' (edge samples come from
+// the polynomial fitted to the first / last window). The hat matrices H5, H9 (row i = weights giving the fitted
+// value at window position i) are built on the host in fp64 and passed by value.
+#include "kernels.cuh"
+
+namespace artalk {
+
+struct SavgolTables { float h5[5][5]; float h9[9][9]; };
+static SavgolTables g_tables;
+static bool g_tables_set = false;
+
+void set_savgol_tables(const float* h5, const float* h9) {
+  for (int i = 0; i < 25; ++i) (&g_tables.h5[0][0])[i] = h5[i];
+  for (int i = 0; i < 81; ++i) (&g_tables.h9[0][0])[i] = h9[i];
+  g_tables_set = true;
+}
+
+template <int W>
+__device__ __forceinline__ float savgol_at(const float* __restrict__ x, int64_t stride, int t, int T, const float (*H)[W]) {
+  constexpr int HALF = W / 2;
+  int row, start;
+  if (t < HALF) { row = t; start = 0; }
+  else if (t >= T - HALF) { row = W - (T - t); start = T - W; }
+  else { row = HALF; start = t - HALF; }
+  float a = 0.f;
+#pragma unroll
+  for (int j = 0; j < W; ++j) a = fmaf(H[row][j], x[(int64_t)(start + j) * stride], a);
+  return a;
+}
+
+__global__ void __launch_bounds__(256) savgol_post_kernel(const float* __restrict__ motion, float* __restrict__ out, int T,
+                                                          int T_out, int dim, int fix_pose, int zero_tail, SavgolTables tb, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % dim);
+    int64_t rt = i / dim;
+    int t = (int)(rt % T_out), clip = (int)(rt / T_out);
+    const float* x = motion + (int64_t)clip * T * dim + c;
+    float v;
+    if (c >= 104 && zero_tail) v = 0.f;                      // inference.py:56
+    else if (c >= 100 && c < 103) v = fix_pose ? 0.f : savgol_at<9>(x, dim, t, T, tb.h9);
+    else v = savgol_at<5>(x, dim, t, T, tb.h5);
+    out[i] = v;
+  }
+}
+
+int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int T_out, int dim, int fix_pose,
+                       int zero_tail, cudaStream_t st) {
+  if (n_clips <= 0 || T_out <= 0) return AT_OK;
+  AT_REQUIRE(g_tables_set, "savgol: tables not set");
+  AT_REQUIRE(T >= 9, "savgol: window_length 9 must be <= number of frames (%d)", T);
+  AT_REQUIRE(T_out <= T && dim == 106, "savgol: bad shape");
+  int64_t total = (int64_t)n_clips * T_out * dim;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  savgol_post_kernel<<<grid, 256, 0, st>>>(motion, out, T, T_out, dim, fix_pose, zero_tail, g_tables, total);
+  AT_LAUNCH_CHECK();
+  return AT_OK;
+}
+
+}  // namespace artalk

@@ -1,0 +1,254 @@
+"""Drop-in for ``app.models.BitwiseARModel`` on the inference path (app/models.py:13-135) and for the parts of
+``BITWISE_VAE`` the engine touches (app/modules/bitwise_vae.py:43-57,78-113). Python only sequences chunks; all
+arithmetic runs in libartalk_b200.so. Differences from the reference that are part of the design:
+
+* batches of clips are accepted (the reference asserts batch 1, app/models.py:65); batched == per-clip loop;
+* wav2vec2 runs for every chunk of every clip up front; the scale loop uses a KV cache, hoisted AdaLN and
+  once-per-chunk previous-chunk K/V — outputs equal the un-cached reference schedule.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .config import ModelConfig, Wav2VecConfig
+from .weights import repack
+
+
+def unpack_words(words: torch.Tensor) -> torch.Tensor:
+    """(...,) int32 words -> (..., 32) int32 bits (reference layout of ``bit_indices``)."""
+    sh = torch.arange(32, device=words.device, dtype=torch.int64)
+    return ((words.to(torch.int64)[..., None] >> sh) & 1).to(torch.int32)
+
+
+def pack_words(bits: torch.Tensor) -> torch.Tensor:
+    sh = torch.arange(32, device=bits.device, dtype=torch.int64)
+    w = (bits.to(torch.int64) << sh).sum(dim=-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+
+
+class BitwiseVAE:
+    """The ``basic_vae`` attribute: bit <-> motion legs and the FLAME adaptor."""
+
+    def __init__(self, owner: "BitwiseARModel"):
+        self._o = owner
+        self.motion_dim = owner.cfg.motion_dim
+        self.code_dim = owner.cfg.code_dim
+        self.patch_nums = list(owner.cfg.patch_nums)
+
+    def get_flame_verts(self, flame_model, shape_params, motion_params, with_global=False):
+        # app/modules/bitwise_vae.py:43-57
+        exp_code, pose_code = motion_params[..., :100], motion_params[..., 100:]
+        if not with_global:
+            pose_code = torch.cat([torch.zeros_like(pose_code[..., :3]), pose_code[..., 3:]], dim=-1)
+        if shape_params.dim() == 2:
+            return flame_model(shape_params=shape_params, expression_params=exp_code, pose_params=pose_code)
+        if shape_params.dim() == 3:
+            return torch.stack([flame_model(shape_params=shape_params[b], expression_params=exp_code[b],
+                                            pose_params=pose_code[b]) for b in range(shape_params.shape[0])], dim=0)
+        raise ValueError("Invalid shape of shape_params: {}".format(shape_params.shape))
+
+    @torch.no_grad()
+    def quant_to_vqidx(self, prev_motion, this_motion=None):
+        """(B,100,106) -> ((B,181,32) int bits, None); the two-motion form is training-only and not on the path."""
+        if this_motion is not None:
+            raise NotImplementedError("quant_to_vqidx(prev, this) is only used in training")
+        words = self._o.motion_to_words(prev_motion)
+        return unpack_words(words), None
+
+    @torch.no_grad()
+    def vqidx_to_motion(self, prev_code_idx, this_code_idx):
+        """Returns (None, new_half): the reference discards the prev half on this path (app/models.py:108)."""
+        return None, self._o.words_to_motion(pack_words(prev_code_idx), pack_words(this_code_idx))
+
+
+class BitwiseARModel:
+    def __init__(self, model_cfg=None, *, device="cuda", precision="bf16", wav2vec: Optional[Wav2VecConfig] = None,
+                 max_clips: int = 256, **kwargs):
+        if isinstance(model_cfg, ModelConfig):
+            self.cfg = model_cfg
+        else:
+            self.cfg = ModelConfig.from_reference_json(model_cfg, wav2vec=wav2vec)
+        self.cfg.validate()
+        if precision not in _lib.PRECISION:
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self._device = torch.device(device)
+        self.max_clips = int(max_clips)
+        self.patch_nums = list(self.cfg.patch_nums)
+        self.attn_depth = self.cfg.ar_depth
+        self.prev_ratio = self.cfg.prev_ratio
+        self.audio_feature_dim = self.cfg.cond_dim
+        self.basic_vae = BitwiseVAE(self)
+        self._h = None
+        self._tensors: Dict[str, torch.Tensor] = {}
+        self._init_words = None
+
+    # ---- nn.Module look-alikes (inference.py:27-28) -------------------------------------------------
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if self._h is not None and torch.device(device) != self._device:
+            raise _lib.ArtalkError("weights already live on %s" % self._device)
+        self._device = torch.device(device)
+        return self
+
+    @property
+    def device(self):
+        return self._device
+
+    def load_state_dict(self, state_dict, strict=True):
+        if not strict:
+            raise ValueError("only strict loading is supported (inference.py:28)")
+        dev = _lib.require_cuda(self._device)
+        lib = _lib.lib()
+        self.close()
+        with torch.cuda.device(dev):
+            self._tensors = repack(state_dict, self.cfg, dev, self.precision)
+            h = C.c_void_p()
+            ccfg = _lib.make_config(self.cfg, self.precision)
+            _lib.check(lib.artalk_create(C.byref(ccfg), C.byref(h)))
+            self._h = h
+            code = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.int32: _lib.I32}
+            for name, t in self._tensors.items():
+                _lib.check(lib.artalk_set_tensor(h, name.encode(), t.data_ptr(), code[t.dtype], t.numel()))
+            _lib.check(lib.artalk_finalize(h))
+            torch.cuda.synchronize(dev)
+        self._init_words = None
+        return self
+
+    def close(self):
+        if self._h is not None:
+            torch.cuda.synchronize(self._device)
+            _lib.lib().artalk_destroy(self._h)
+            self._h = None
+        self._tensors = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_workspace_limit(self, n_bytes: int):
+        _lib.check(_lib.lib().artalk_set_workspace_limit(self._handle(), n_bytes))
+
+    def _handle(self):
+        if self._h is None:
+            raise _lib.ArtalkError("no weights loaded: call load_state_dict first")
+        return self._h
+
+    # ---- stage-level calls (each is one C-ABI call) ---------------------------------------------------
+    def _dev(self, t, dtype=torch.float32):
+        return t.to(self._device, dtype).contiguous()
+
+    def audio_cond(self, chunks: torch.Tensor) -> torch.Tensor:
+        """(N, 64000) audio chunks -> (N, 181, 1024) conditioning (wav2vec2 + area pooling)."""
+        x = self._dev(chunks)
+        if x.dim() != 2 or x.shape[1] != self.cfg.chunk_samples:
+            raise ValueError("expected (N, %d) chunks, got %s" % (self.cfg.chunk_samples, tuple(x.shape)))
+        cond = torch.empty(x.shape[0], self.cfg.seq_tokens, self.cfg.cond_dim, device=self._device)
+        _lib.check(_lib.lib().artalk_audio_encode(self._handle(), x.data_ptr(), x.shape[0], cond.data_ptr(),
+                                                  _lib.stream_ptr(self._device)))
+        return cond
+
+    def style_cond(self, style_motion: Optional[torch.Tensor], batch: int) -> torch.Tensor:
+        """(B,50,106) or None -> (B,768) style token (app/models.py:67-73)."""
+        if style_motion is None:
+            return self._tensors["style.null"][None].expand(batch, -1).contiguous()
+        s = self._dev(style_motion)
+        if s.dim() != 3 or s.shape[0] != batch or s.shape[1] != self.cfg.style_len or s.shape[2] != self.cfg.motion_dim:
+            raise ValueError("style_motion must be (%d, %d, %d), got %s" % (batch, self.cfg.style_len, self.cfg.motion_dim, tuple(s.shape)))
+        out = torch.empty(batch, self.cfg.embed_dim, device=self._device)
+        _lib.check(_lib.lib().artalk_style_encode(self._handle(), s.data_ptr(), batch, out.data_ptr(), _lib.stream_ptr(self._device)))
+        return out
+
+    def motion_to_words(self, motion: torch.Tensor, enc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        m = self._dev(motion)
+        words = torch.empty(m.shape[0], self.cfg.seq_tokens, dtype=torch.int32, device=self._device)
+        _lib.check(_lib.lib().artalk_motion_to_bits(self._handle(), m.data_ptr(), m.shape[0], words.data_ptr(), _lib.ptr(enc_out),
+                                                    _lib.stream_ptr(self._device)))
+        return words
+
+    def words_to_motion(self, prev_words: torch.Tensor, words: torch.Tensor) -> torch.Tensor:
+        pw, w = self._dev(prev_words, torch.int32), self._dev(words, torch.int32)
+        out = torch.empty(w.shape[0], self.cfg.chunk_frames, self.cfg.motion_dim, device=self._device)
+        _lib.check(_lib.lib().artalk_bits_to_motion(self._handle(), pw.data_ptr(), w.data_ptr(), w.shape[0], out.data_ptr(),
+                                                    _lib.stream_ptr(self._device)))
+        return out
+
+    def initial_words(self, batch: int) -> torch.Tensor:
+        """Bits of the all-zero previous motion (app/models.py:86-87); input independent, cached per weight set."""
+        if self._init_words is None:
+            z = torch.zeros(1, self.cfg.chunk_frames, self.cfg.motion_dim, device=self._device)
+            self._init_words = self.motion_to_words(z)
+        return self._init_words.expand(batch, -1).contiguous()
+
+    def ar_chunk(self, cond: torch.Tensor, style: torch.Tensor, prev_words: torch.Tensor, motion_out: torch.Tensor,
+                 words_out=None, logits_out=None, forced_words=None, enc_out=None):
+        """One chunk for all clips; ``cond`` is (B,181,1024) possibly a strided view over clips; prev_words updated in place."""
+        B = style.shape[0]
+        assert cond.stride(2) == 1 and cond.stride(1) == self.cfg.cond_dim
+        _lib.check(_lib.lib().artalk_ar_chunk(
+            self._handle(), B, cond.data_ptr(), cond.stride(0), style.data_ptr(), prev_words.data_ptr(), motion_out.data_ptr(),
+            _lib.ptr(words_out), _lib.ptr(logits_out), _lib.ptr(forced_words), _lib.ptr(enc_out), _lib.stream_ptr(self._device)))
+
+    # ---- app/models.py:62-121 -------------------------------------------------------------------------
+    @torch.no_grad()
+    def inference(self, batch, with_gtmotion=False, trace: Optional[dict] = None, teacher_words: Optional[torch.Tensor] = None):
+        cfg = self.cfg
+        audio = batch["audio"]
+        if audio.dim() != 2:
+            raise ValueError("batch['audio'] must be (B, S)")
+        B, S = audio.shape
+        style_motion = batch.get("style_motion", None)
+        seq_length = cfg.frames_for_samples(S)
+        T = cfg.chunk_frames
+        n_chunks = math.ceil(seq_length / T)
+        if n_chunks == 0:
+            return torch.zeros(B, 0, cfg.motion_dim, device=self._device)
+        audio = self._dev(audio)
+        pad = n_chunks * cfg.chunk_samples - S
+        if pad:
+            audio = torch.cat([audio, audio.new_zeros(B, pad)], dim=-1)
+        cond = self.audio_cond(audio.view(B * n_chunks, cfg.chunk_samples)).view(B, n_chunks, cfg.seq_tokens, cfg.cond_dim)
+        style = self.style_cond(style_motion, B)
+        motion = torch.empty(B, n_chunks, T, cfg.motion_dim, device=self._device)
+        if trace is not None:
+            trace.update(cond=cond, style=style,
+                         logits=torch.empty(B, n_chunks, cfg.seq_tokens, 2 * cfg.code_dim, device=self._device),
+                         words=torch.empty(B, n_chunks, cfg.seq_tokens, dtype=torch.int32, device=self._device),
+                         prev_words=torch.empty(B, n_chunks, cfg.seq_tokens, dtype=torch.int32, device=self._device),
+                         enc_out=torch.empty(B, n_chunks, T, cfg.code_dim, device=self._device))
+        for b0 in range(0, B, self.max_clips):
+            b1 = min(B, b0 + self.max_clips)
+            nb = b1 - b0
+            prev_words = self.initial_words(nb)
+            chunk_out = torch.empty(nb, T, cfg.motion_dim, device=self._device)
+            tr = None
+            if trace is not None:
+                tr = dict(logits=torch.empty(nb, cfg.seq_tokens, 2 * cfg.code_dim, device=self._device),
+                          words=torch.empty(nb, cfg.seq_tokens, dtype=torch.int32, device=self._device),
+                          enc=torch.empty(nb, T, cfg.code_dim, device=self._device))
+            for c in range(n_chunks):
+                forced = None
+                if teacher_words is not None:
+                    forced = teacher_words[b0:b1, c].to(self._device, torch.int32).contiguous()
+                self.ar_chunk(cond[b0:b1, c], style[b0:b1], prev_words, chunk_out,
+                              words_out=None if tr is None else tr["words"], logits_out=None if tr is None else tr["logits"],
+                              forced_words=forced, enc_out=None if tr is None else tr["enc"])
+                motion[b0:b1, c].copy_(chunk_out)
+                if tr is not None:
+                    trace["logits"][b0:b1, c].copy_(tr["logits"]); trace["words"][b0:b1, c].copy_(tr["words"])
+                    trace["prev_words"][b0:b1, c].copy_(prev_words); trace["enc_out"][b0:b1, c].copy_(tr["enc"])
+        pred_motions = motion.view(B, n_chunks * T, cfg.motion_dim)[:, :seq_length]
+        if with_gtmotion:
+            min_length = min(batch["motion"].shape[1], pred_motions.shape[1])
+            shape_code = batch["shape"].expand(-1, min_length, -1)
+            return pred_motions[:, :min_length], batch["motion"][:, :min_length], shape_code
+        return pred_motions

@@ -1,0 +1,152 @@
+/* artalk_b200 — C ABI of the B200-native ARTalk audio->motion path (libartalk_b200.so).
+ *
+ * The reference (zsc/ARTalk) has no native code, plugin registry or FFI: its boundary for this path is the Python
+ * surface ARTAvatarInferEngine / BitwiseARModel.inference / BITWISE_VAE.get_flame_verts / FLAMEModel.forward. The Python
+ * mirror of that surface lives in artalk_b200/{engine,model,flame}.py and binds exactly the entry points declared here
+ * with ctypes; each entry point cites the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every pointer is a DEVICE pointer unless named host_*;
+ * tensors are dense row-major; `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are
+ * asynchronous on that stream; return value 0 = ok, otherwise an ARTALK_E* code with text in artalk_last_error().
+ * An engine is not thread-safe; different engines may be used concurrently. Tensor memory handed to
+ * artalk_set_tensor stays owned by the caller and must outlive the engine.
+ */
+#ifndef ARTALK_B200_H
+#define ARTALK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARTALK_OK 0
+#define ARTALK_EINVAL 1    /* bad argument / unsupported shape */
+#define ARTALK_ECUDA 2     /* CUDA runtime error */
+#define ARTALK_ENOMEM 3    /* workspace allocation failed */
+#define ARTALK_EMISSING 4  /* artalk_finalize: a required tensor was not provided (strict load) */
+#define ARTALK_ESTATE 5
+
+#define ARTALK_F32 0
+#define ARTALK_BF16 1
+#define ARTALK_I32 2
+
+#define ARTALK_PRECISION_FP32 0 /* CUDA-core fp32 GEMMs; parity tolerance 1e-3 */
+#define ARTALK_PRECISION_BF16 1 /* tcgen05 bf16 GEMMs, fp32 accumulate; parity tolerance 2e-2 */
+
+typedef struct artalk_engine artalk_engine_t;
+
+/* assets/config.json:1-15 + the constants hard-coded at app/models.py:19,22,27,37,41-42 + the XLS-R-300m Wav2Vec2Config */
+typedef struct artalk_config {
+  int precision;
+  int ar_depth, ar_heads, embed_dim, cond_dim;
+  int vae_depth, vae_heads, vae_hidden, code_dim, motion_dim;
+  int n_levels;
+  int patch_nums[8];
+  int w2v_layers, w2v_heads, w2v_hidden, w2v_ffn, w2v_conv_dim, w2v_n_conv;
+  int w2v_conv_kernel[8];
+  int w2v_conv_stride[8];
+  int w2v_pos_kernel, w2v_pos_groups;
+  int style_dim, style_layers, style_heads, style_ffn, style_len;
+  int chunk_samples;
+  float w2v_ln_eps;
+} artalk_config_t;
+
+const char* artalk_last_error(void);
+int artalk_abi_version(void);
+
+/* --- engine life cycle: replaces BitwiseARModel.__init__ + load_state_dict(strict=True) (inference.py:24-28) --- */
+int artalk_create(const artalk_config_t* cfg, artalk_engine_t** out);
+int artalk_destroy(artalk_engine_t* e);
+/* register one repacked weight / table by canonical name (see artalk_b200/weights.py for the name list) */
+int artalk_set_tensor(artalk_engine_t* e, const char* name, void* ptr, int dtype, int64_t numel);
+/* strict check that every tensor the path needs is present with the right dtype and size */
+int artalk_finalize(artalk_engine_t* e);
+/* soft budget (bytes) used to size wav2vec sub-batches; the library grows its device workspace on demand */
+int artalk_set_workspace_limit(artalk_engine_t* e, size_t bytes);
+size_t artalk_workspace_bytes(const artalk_engine_t* e);
+
+/* --- Wav2Vec2Model.forward + multi-scale area pooling (app/modules/wav2vec.py:11-27, app/models.py:93-95) ---
+ * audio [n_chunks, chunk_samples] f32 (each row normalised on its own) -> cond [n_chunks, 181, 1024] f32 */
+int artalk_audio_encode(artalk_engine_t* e, const float* audio, int n_chunks, float* cond, void* stream);
+
+/* --- StyleEncoder + style_cond_embed + 1.1/-0.1 mix (app/modules/style_encoder.py:26-42, app/models.py:67-70) ---
+ * style_motion [n_clips, 50, 106] f32 -> style [n_clips, 768] f32 */
+int artalk_style_encode(artalk_engine_t* e, const float* style_motion, int n_clips, float* style, void* stream);
+
+/* --- BITWISE_VAE.quant_to_vqidx(prev, None) (app/modules/bitwise_vae.py:78-93) ---
+ * motion [n_clips, 100, 106] f32 -> words [n_clips, 181] u32 (bit j of a word = code dim j); enc_out (nullable)
+ * receives the encoder output [n_clips, 100, 32] f32 */
+int artalk_motion_to_bits(artalk_engine_t* e, const float* motion, int n_clips, uint32_t* words, float* enc_out, void* stream);
+
+/* --- BITWISE_VAE.vqidx_to_motion (app/modules/bitwise_vae.py:105-113): returns the new half [n_clips, 100, 106] --- */
+int artalk_bits_to_motion(artalk_engine_t* e, const uint32_t* prev_words, const uint32_t* words, int n_clips, float* motion,
+                          void* stream);
+
+/* --- one chunk of BitwiseARModel.inference's loop body (app/models.py:93-114) for n_clips clips at once ---
+ * cond: clip b's [181,1024] block at cond + b*cond_clip_stride ; style [n_clips,768] ;
+ * prev_words [n_clips,181] in: re-encoded bits of the previous chunk, out: those of this chunk ;
+ * motion_out [n_clips,100,106] ; words_out / logits_out [n_clips,181,64] / enc_out nullable ;
+ * forced_words (nullable) [n_clips,181]: teacher forcing — next-scale inputs and the decode use these bits. */
+int artalk_ar_chunk(artalk_engine_t* e, int n_clips, const float* cond, int64_t cond_clip_stride, const float* style,
+                    uint32_t* prev_words, float* motion_out, uint32_t* words_out, float* logits_out,
+                    const uint32_t* forced_words, float* enc_out, void* stream);
+
+/* --- FLAMEModel.forward / lbs (app/flame_model/FLAME.py:117-149, app/flame_model/lbs.py:142-383) --- */
+typedef struct artalk_flame_model {
+  int n_verts, n_shape, n_exp;
+  const float* v_template;   /* [V*3] */
+  const float* dirs;         /* [n_shape+n_exp+36][V*3]: shape, expression then pose-corrective bases */
+  const float* j_template;   /* [15]  J_regressor @ v_template */
+  const float* j_dirs;       /* [n_shape+n_exp][15] */
+  const float* lbs_weights;  /* [V][5] */
+  int parents[5];
+  float scale;
+} artalk_flame_model_t;
+size_t artalk_flame_workspace_floats(const artalk_flame_model_t* fm, int n_frames);
+/* shape [n, n_shape] (row stride shape_stride, 0 = one shared row), expr [n, n_exp], pose [n, 6] = (global rot, jaw);
+ * zero_global != 0 drops the global rotation (get_flame_verts with_global=False, bitwise_vae.py:45-46) */
+int artalk_flame_vertices(const artalk_flame_model_t* fm, const float* shape, int64_t shape_stride, const float* expr,
+                          int64_t expr_stride, const float* pose, int64_t pose_stride, int zero_global, float* workspace,
+                          float* verts, int n_frames, void* stream);
+
+/* --- smooth_motion_savgol + [:clip_length] + pose / eye zeroing (inference.py:52-56,89-95) ---
+ * host_h5 [5*5], host_h9 [9*9]: hat matrices of the window-5/poly-2 and window-9/poly-3 fits (host pointers) */
+int artalk_set_savgol_tables(const float* host_h5, const float* host_h9);
+/* fix_pose: zero dims 100:103 (inference.py:53-54); zero_tail: zero dims 104:106 (inference.py:56) */
+int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_frames, int n_frames_out, int fix_pose,
+                         int zero_tail, void* stream);
+
+/* ---------------- operator-level entry points (unit parity tests of single kernels) ---------------- */
+typedef struct artalk_rowmap { int rpb; int64_t bs, rs; } artalk_rowmap_t;
+typedef struct artalk_gemm {
+  const void* A; artalk_rowmap_t a_map;
+  const void* W; int64_t ldw;
+  int M, N, K;
+  int tap_w, tap_pad;
+  int groups; int64_t a_gs, w_gs, c_gs; int bias_gs;
+  const float* bias;
+  int act;                       /* 0 none, 1 gelu(erf), 2 gelu(tanh), 3 leaky_relu(0.2), 4 silu */
+  const void* gate; int gate_dt; artalk_rowmap_t gate_map;
+  const float* resid; artalk_rowmap_t resid_map;
+  float* out32; void* out_act; int out_act_dt; artalk_rowmap_t c_map;
+} artalk_gemm_t;
+/* out = resid + gate * act(A W^T + bias); precision selects the fp32 CUDA-core or the bf16 tcgen05 kernel */
+int artalk_op_gemm(const artalk_gemm_t* g, int precision, void* stream);
+
+typedef struct artalk_attn {
+  const void* q; const void* k; const void* v; void* out;
+  int dt, n_seq, n_heads, head_dim, lq, lk;
+  int64_t q_ss, q_rs, k_ss, k_rs, v_ss, v_rs, o_ss, o_rs;
+  float scale;
+  int split;
+} artalk_attn_t;
+int artalk_op_attention(const artalk_attn_t* a, void* stream);
+int artalk_op_layernorm(const float* x, void* out, int out_dt, const float* gamma, const float* beta, int rows, int cols,
+                        float eps, int act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARTALK_B200_H */

@@ -1,0 +1,178 @@
+"""GPU: single-kernel parity through the C ABI (artalk_op_* entry points) against plain torch fp32 on the device."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from artalk_b200 import _lib  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rowmap(rpb=0, bs=0, rs=0):
+    return _lib.RowMap(rpb, bs, rs)
+
+
+def run_gemm(precision, A, W, M, N, K, *, a_map=None, bias=None, act=0, gate=None, gate_map=None, resid=None,
+             resid_map=None, out32=None, out_act=None, c_map=None, tap_w=0, tap_pad=0, groups=1, a_gs=0, w_gs=0, c_gs=0,
+             bias_gs=0, ldw=None):
+    g = _lib.Gemm()
+    g.A, g.W = A.data_ptr(), W.data_ptr()
+    g.a_map = a_map or rowmap(0, 0, K)
+    g.ldw = ldw if ldw is not None else K
+    g.M, g.N, g.K = M, N, K
+    g.tap_w, g.tap_pad, g.groups, g.a_gs, g.w_gs, g.c_gs, g.bias_gs = tap_w, tap_pad, groups, a_gs, w_gs, c_gs, bias_gs
+    g.bias = _lib.ptr(bias)
+    g.act = act
+    g.gate = _lib.ptr(gate)
+    g.gate_dt = _lib.F32 if gate is None or gate.dtype == torch.float32 else _lib.BF16
+    g.gate_map = gate_map or rowmap(0, 0, N)
+    g.resid = _lib.ptr(resid)
+    g.resid_map = resid_map or rowmap(0, 0, N)
+    g.out32 = _lib.ptr(out32)
+    g.out_act = _lib.ptr(out_act)
+    g.out_act_dt = _lib.F32 if out_act is None or out_act.dtype == torch.float32 else _lib.BF16
+    g.c_map = c_map or rowmap(0, 0, N)
+    _lib.check(_lib.lib().artalk_op_gemm(C.byref(g), precision, _lib.stream_ptr(dev())))
+    torch.cuda.synchronize()
+
+
+ACTS = {0: lambda x: x, 1: F.gelu, 2: lambda x: F.gelu(x, approximate="tanh"), 3: lambda x: F.leaky_relu(x, 0.2), 4: F.silu}
+
+
+def precisions():
+    return [("fp32", 0, torch.float32, 2e-4), ("bf16", 1, torch.bfloat16, 3e-2)]
+
+
+@pytest.mark.parametrize("pname,prec,dt,tol", precisions())
+@pytest.mark.parametrize("M,N,K,act", [(300, 768, 768, 0), (77, 2304, 768, 2), (1, 64, 768, 0), (200, 106, 512, 0),
+                                       (513, 512, 32, 3), (129, 1024, 4096, 1), (256, 32, 512, 0), (100, 4608, 1024, 4)])
+def test_gemm_bias_act(pname, prec, dt, tol, M, N, K, act):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g).to(dev(), dt)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev(), dt)
+    b = torch.randn(N, generator=g).to(dev())
+    out = torch.full((M, N), float("nan"), device=dev())
+    run_gemm(prec, A, W, M, N, K, bias=b, act=act, out32=out)
+    ref = ACTS[act](A.float() @ W.float().t() + b)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("pname,prec,dt,tol", precisions())
+def test_gemm_gate_residual_rowmaps(pname, prec, dt, tol):
+    """AR epilogue: x += (A W^T + b) * gamma with gamma rows gathered through (clip, token) maps; dual outputs."""
+    B, n_new, L, C, K = 3, 25, 181, 768, 3072
+    M = B * n_new
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = torch.randn(M, K, generator=g).to(dev(), dt)
+    W = (torch.randn(C, K, generator=g) / math.sqrt(K)).to(dev(), dt)
+    b = torch.randn(C, generator=g).to(dev())
+    n_ada = 6 * C
+    ada = torch.randn(B, L, n_ada, generator=g).to(dev(), dt)
+    off = 31
+    x = torch.randn(M, C, generator=g).to(dev())
+    x0 = x.clone()
+    xa = torch.empty(M, C, device=dev(), dtype=dt)
+    gate_view = ada[:, off:off + n_new, C:2 * C]                   # gamma2 slice
+    gate_ptr_t = ada.view(-1)[off * n_ada + C:]
+    run_gemm(prec, A, W, M, C, K, bias=b, gate=gate_ptr_t, gate_map=rowmap(n_new, L * n_ada, n_ada), resid=x, out32=x,
+             out_act=xa)
+    ref = x0 + (A.float() @ W.float().t() + b) * gate_view.reshape(M, C).float()
+    scale = max(1.0, ref.abs().max().item())
+    assert (x - ref).abs().max().item() < tol * scale
+    assert (xa.float() - ref).abs().max().item() < (tol + (0 if dt == torch.float32 else 8e-3)) * scale
+
+
+@pytest.mark.parametrize("pname,prec,dt,tol", precisions())
+@pytest.mark.parametrize("k,s", [(3, 2), (2, 2)])
+def test_conv_as_overlapping_row_gemm(pname, prec, dt, tol, k, s):
+    """wav2vec conv layers 1-6: channels-last implicit GEMM with overlapping A rows == F.conv1d."""
+    n, L_in, Cc = 3, 401, 512
+    L_out = (L_in - k) // s + 1
+    g = torch.Generator(device="cpu").manual_seed(k)
+    x = torch.randn(n, L_in, Cc, generator=g).to(dev(), dt)                      # channels last
+    w = (torch.randn(Cc, Cc, k, generator=g) / math.sqrt(Cc * k)).to(dev(), dt)   # torch layout (out,in,k)
+    b = torch.randn(Cc, generator=g).to(dev())
+    wp = w.permute(0, 2, 1).reshape(Cc, k * Cc).contiguous()
+    out = torch.empty(n * L_out, Cc, device=dev())
+    run_gemm(prec, x, wp, n * L_out, Cc, k * Cc, a_map=rowmap(L_out, L_in * Cc, s * Cc), bias=b, out32=out)
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), b, stride=s).transpose(1, 2).reshape(n * L_out, Cc)
+    assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("pname,prec,dt,tol", precisions())
+def test_pos_conv_grouped_tap_gemm(pname, prec, dt, tol):
+    """wav2vec positional conv: grouped conv1d k=128 pad 64 (last sample dropped) + GELU + residual."""
+    n, Fr, H, G, K = 2, 199, 1024, 16, 128
+    gw = H // G
+    g = torch.Generator(device="cpu").manual_seed(11)
+    h = torch.randn(n, Fr, H, generator=g).to(dev())
+    w = (torch.randn(H, gw, K, generator=g) / math.sqrt(gw * K)).to(dev())
+    b = torch.randn(H, generator=g).to(dev())
+    A = h.to(dt)
+    wp = w.view(G, gw, gw, K).permute(0, 1, 3, 2).reshape(G, gw, K * gw).contiguous().to(dt)
+    out = torch.empty(n * Fr, H, device=dev())
+    run_gemm(prec, A, wp, n * Fr, gw, K * gw, a_map=rowmap(Fr, Fr * H, H), tap_w=gw, tap_pad=K // 2, groups=G, a_gs=gw,
+             w_gs=gw * K * gw, c_gs=gw, bias_gs=gw, bias=b, act=1, resid=h.view(-1, H), resid_map=rowmap(0, 0, H),
+             out32=out, c_map=rowmap(0, 0, H), ldw=K * gw)
+    pc = F.conv1d(A.float().transpose(1, 2), w.to(dt).float(), b, padding=K // 2, groups=G)[:, :, :-1]
+    ref = (h + F.gelu(pc).transpose(1, 2)).reshape(n * Fr, H)
+    assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+def run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, scale, split=0):
+    a = _lib.Attn()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.dt = _lib.F32 if q.dtype == torch.float32 else _lib.BF16
+    a.n_seq, a.n_heads, a.head_dim, a.lq, a.lk = n_seq, H, D, lq, lk
+    (a.q_ss, a.q_rs, a.k_ss, a.k_rs, a.v_ss, a.v_rs, a.o_ss, a.o_rs) = strides
+    a.scale, a.split = scale, split
+    _lib.check(_lib.lib().artalk_op_attention(C.byref(a), _lib.stream_ptr(dev())))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("n_seq,H,D,lq,lk,split", [(3, 16, 64, 199, 199, 0), (2, 8, 64, 200, 200, 100), (4, 12, 64, 25, 212, 0),
+                                                   (5, 12, 64, 1, 182, 0), (2, 4, 32, 50, 50, 0), (2, 12, 64, 100, 362, 0)])
+def test_attention(dt, tol, n_seq, H, D, lq, lk, split):
+    g = torch.Generator(device="cpu").manual_seed(lq * 3 + lk)
+    Cw = H * D
+    q = torch.randn(n_seq, lq, Cw, generator=g).to(dev(), dt)
+    k = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), dt)
+    v = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), dt)
+    out = torch.empty(n_seq, lq, Cw, device=dev(), dtype=dt)
+    scale = 0.3
+    run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), scale, split)
+    qq = q.float().view(n_seq, lq, H, D).transpose(1, 2)
+    kk = k.float().view(n_seq, lk, H, D).transpose(1, 2)
+    vv = v.float().view(n_seq, lk, H, D).transpose(1, 2)
+    s = qq @ kk.transpose(-1, -2) * scale
+    if split:
+        m = torch.zeros(lq, lk, device=dev())
+        m[:split, split:] = -math.inf
+        s = s + m
+    ref = (torch.softmax(s, -1) @ vv).transpose(1, 2).reshape(n_seq, lq, Cw)
+    assert (out.float() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("cols,act", [(512, 1), (1024, 0), (768, 0), (128, 0)])
+def test_layernorm(cols, act):
+    g = torch.Generator(device="cpu").manual_seed(cols)
+    x = (3 * torch.randn(333, cols, generator=g) + 1.5).to(dev())
+    gam, bet = torch.randn(cols, generator=g).to(dev()), torch.randn(cols, generator=g).to(dev())
+    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 3e-2)):
+        out = torch.empty(333, cols, device=dev(), dtype=dt)
+        _lib.check(_lib.lib().artalk_op_layernorm(x.data_ptr(), out.data_ptr(), _lib.F32 if dt == torch.float32 else _lib.BF16,
+                                                  gam.data_ptr(), bet.data_ptr(), 333, cols, 1e-5, act, _lib.stream_ptr(dev())))
+        torch.cuda.synchronize()
+        ref = F.layer_norm(x, (cols,), gam, bet, 1e-5)
+        if act:
+            ref = F.gelu(ref)
+        assert (out.float() - ref).abs().max().item() < tol

@@ -1,0 +1,272 @@
+"""GPU: parity of the CUDA path (called through the reference-shaped Python surface -> C ABI) against the oracle on
+the same seeded inputs, and against the golden fixtures written from the live reference.
+
+Tolerances (BASELINE.json north star): fp32 mode — bits exact where the logit margin > 1e-3, motion / vertices
+within 1e-3 abs; bf16 mode — motion within 2e-2 abs, bits exact where the margin clears the bf16 noise floor
+(checked teacher-forced so that one flip does not cascade through the recurrence)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from artalk_b200 import config, synthetic  # noqa: E402
+from artalk_b200.model import BitwiseARModel, unpack_words, pack_words  # noqa: E402
+from artalk_b200.flame import FLAMEModel  # noqa: E402
+from artalk_b200.engine import ARTAvatarInferEngine, smooth_motion  # noqa: E402
+from oracle.artalk_oracle import Oracle, get_flame_verts  # noqa: E402
+from oracle.cases import CASES, flame_inputs  # noqa: E402
+import golden_util as gu  # noqa: E402
+
+DEV = "cuda:0"
+torch.set_num_threads(os.cpu_count() or 1)
+
+MOTION_TOL = {"fp32": 1e-3, "bf16": 2e-2}
+LOGIT_TOL = {"fp32": 2e-3, "bf16": 0.25}
+BIT_MARGIN = {"fp32": 1e-3, "bf16": 0.25}
+
+_models = {}
+
+
+def model(cfg_name, precision):
+    key = (cfg_name, precision)
+    if key not in _models:
+        _models.clear()                    # one resident weight set at a time
+        torch.cuda.empty_cache()
+        m = BitwiseARModel(getattr(config, cfg_name), device=DEV, precision=precision)
+        m.load_state_dict(gu.state_dict(cfg_name))
+        _models[key] = m
+    return _models[key]
+
+
+def oracle(cfg_name):
+    return Oracle(gu.state_dict(cfg_name), getattr(config, cfg_name))
+
+
+# ----------------------------------------------------------------------------- stages
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_audio_cond_matches_oracle(precision):
+    m, o = model("TINY", precision), oracle("TINY")
+    audio = synthetic.make_audio(3, 64000)
+    audio[2, 40000:] = 0.0                                   # zero-padded tail is normalised with the chunk (quirk 4)
+    with torch.no_grad():
+        ref = o.audio_cond(o.audio_encode(audio))
+    got = m.audio_cond(audio).cpu()
+    tol = 2e-3 if precision == "fp32" else 0.15
+    assert got.shape == (3, 181, 1024)
+    assert (got - ref).abs().max().item() < tol, (got - ref).abs().max().item()
+    assert (got - ref).abs().mean().item() < tol / 10
+
+
+def test_style_cond_matches_oracle():
+    m, o = model("TINY", "fp32"), oracle("TINY")
+    sm = synthetic.make_style_motion(4)
+    with torch.no_grad():
+        ref = o.style_cond(sm, 4)[:, 0]
+    got = m.style_cond(sm, 4).cpu()
+    assert (got - ref).abs().max().item() < 1e-4
+    null = m.style_cond(None, 2).cpu()
+    assert torch.equal(null[0], gu.state_dict("TINY")["null_style_cond"].reshape(-1))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vae_legs_match_oracle(precision):
+    m, o = model("TINY", precision), oracle("TINY")
+    g = torch.Generator().manual_seed(3)
+    bits_prev = torch.randint(0, 2, (3, 181, 32), generator=g, dtype=torch.int32)
+    bits = torch.randint(0, 2, (3, 181, 32), generator=g, dtype=torch.int32)
+    with torch.no_grad():
+        ref_motion = o.vae_decode(bits_prev, bits)
+        ref_enc = o.vae_encode(ref_motion)
+        ref_bits = o.bsq_bits(ref_enc)
+    got = m.words_to_motion(pack_words(bits_prev), pack_words(bits)).cpu()
+    assert (got - ref_motion).abs().max().item() < MOTION_TOL[precision]
+    enc = torch.empty(3, 100, 32, device=DEV)
+    words = m.motion_to_words(ref_motion, enc_out=enc)
+    tol = 2e-3 if precision == "fp32" else 0.1
+    assert (enc.cpu() - ref_enc).abs().max().item() < tol
+    got_bits = unpack_words(words).cpu()
+    frac = (got_bits != ref_bits).float().mean().item()
+    assert frac < (2e-3 if precision == "fp32" else 0.08), frac
+    # drop-in surface of basic_vae
+    b2, none = m.basic_vae.quant_to_vqidx(ref_motion)
+    assert none is None and b2.shape == (3, 181, 32) and torch.equal(b2.cpu(), got_bits)
+
+
+def test_bsq_bits_exact_given_same_encoder_output():
+    """The residual quantiser itself is bit exact: feed the CUDA path's own encoder output to the oracle's BSQ."""
+    m, o = model("TINY", "fp32"), oracle("TINY")
+    motion = 0.3 * torch.randn(5, 100, 106, generator=torch.Generator().manual_seed(9))
+    enc = torch.empty(5, 100, 32, device=DEV)
+    words = m.motion_to_words(motion, enc_out=enc)
+    ref_bits = o.bsq_bits(enc.cpu())
+    got = unpack_words(words).cpu()
+    zs = enc.cpu().abs()
+    assert (got != ref_bits).float().mean().item() < 5e-4          # only |residual| ~ 1e-7 sign ties may differ
+
+
+# ----------------------------------------------------------------------------- end to end vs golden (fp32)
+@pytest.mark.parametrize("name", ["tiny_style", "tiny_null", "tiny_ragged", "full_10s"])
+def test_inference_matches_reference_golden_fp32(name):
+    case = CASES[name]
+    g = gu.load(name)
+    m = model(case.cfg_name, "fp32")
+    tr = {}
+    out = m.inference({"audio": case.audio(), "style_motion": case.style()}, trace=tr)
+    assert tuple(out.shape) == g["motion"].shape
+    safe = gu.margins(g["logits"]) > 1e-3
+    bits = unpack_words(tr["words"]).cpu()
+    gb = gu.unpack_bits(g["bits"])
+    assert int(((bits != gb) & safe).sum()) == 0                    # sampled bits exact where margin > 1e-3
+    np.testing.assert_allclose(tr["logits"].cpu().numpy(), g["logits"], atol=LOGIT_TOL["fp32"], rtol=0)
+    np.testing.assert_allclose(out.cpu().numpy(), g["motion"], atol=MOTION_TOL["fp32"], rtol=0)
+    np.testing.assert_allclose(tr["cond"].cpu()[..., ::gu.COND_STRIDE].numpy(), g["cond_slice"], atol=2e-3, rtol=0)
+    np.testing.assert_allclose(tr["style"].cpu().numpy(), g["style"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(tr["enc_out"].cpu().numpy(), g["enc_out"], atol=5e-3, rtol=0)
+    assert (unpack_words(tr["prev_words"]).cpu() != gu.unpack_bits(g["prev_bits"])).float().mean().item() < 5e-3
+
+
+# ----------------------------------------------------------------------------- bf16: teacher forced + free running
+@pytest.mark.parametrize("name", ["tiny_style", "full_10s"])
+def test_inference_bf16_teacher_forced(name):
+    case = CASES[name]
+    g = gu.load(name)
+    m = model(case.cfg_name, "bf16")
+    tr = {}
+    gold_words = torch.from_numpy(g["bits"].view(np.int32).copy())                   # (B, n_chunks, 181) u32 -> i32 bits
+    out = m.inference({"audio": case.audio(), "style_motion": case.style()}, trace=tr, teacher_words=gold_words)
+    lg = tr["logits"].cpu().numpy()
+    assert np.abs(lg - g["logits"]).max() < LOGIT_TOL["bf16"]
+    safe = gu.margins(g["logits"]) > BIT_MARGIN["bf16"]
+    bits = unpack_words(tr["words"]).cpu()
+    gb = gu.unpack_bits(g["bits"])
+    assert int(((bits != gb) & safe).sum()) == 0
+    # first chunk has no dependence on re-encoded bits: motion within the bf16 tolerance of the reference
+    n0 = min(100, g["motion"].shape[1])
+    assert np.abs(out.cpu().numpy()[:, :n0] - g["motion"][:, :n0]).max() < MOTION_TOL["bf16"]
+
+
+@pytest.mark.parametrize("name", ["tiny_style", "full_10s"])
+def test_inference_bf16_free_running(name):
+    case = CASES[name]
+    g = gu.load(name)
+    m = model(case.cfg_name, "bf16")
+    out = m.inference({"audio": case.audio(), "style_motion": case.style()}).cpu().numpy()
+    assert np.isfinite(out).all()
+    assert np.abs(out - g["motion"]).max() < MOTION_TOL["bf16"] * 2.5      # bit flips compound over chunks
+    assert np.abs(out - g["motion"]).mean() < 5e-3
+
+
+# ----------------------------------------------------------------------------- properties
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batched_equals_per_clip_loop(precision):
+    case = CASES["tiny_style"]
+    m = model("TINY", precision)
+    a, s = case.audio(), case.style()
+    both = m.inference({"audio": a, "style_motion": s})
+    for b in range(2):
+        one = m.inference({"audio": a[b:b + 1], "style_motion": s[b:b + 1]})
+        assert torch.equal(both[b:b + 1], one)                     # same kernels, same per-row arithmetic
+
+
+def test_clip_subbatching_and_empty():
+    case = CASES["tiny_style"]
+    m = model("TINY", "fp32")
+    a, s = case.audio(), case.style()
+    ref = m.inference({"audio": a, "style_motion": s})
+    m.max_clips = 1
+    try:
+        got = m.inference({"audio": a, "style_motion": s})
+    finally:
+        m.max_clips = 256
+    assert torch.equal(ref, got)
+    assert m.inference({"audio": torch.zeros(1, 0)}).shape == (1, 0, 106)
+    short = m.inference({"audio": a[:1, :100]})                  # 100 samples -> ceil(100/640) = 1 frame
+    assert short.shape == (1, 1, 106)
+
+
+def test_strict_state_dict():
+    from artalk_b200.weights import CheckpointError
+    sd = dict(gu.state_dict("TINY"))
+    m = BitwiseARModel(config.TINY, device=DEV, precision="fp32")
+    bad = dict(sd); bad.pop("logits_head.bias")
+    with pytest.raises(CheckpointError):
+        m.load_state_dict(bad)
+    bad = dict(sd); bad["extra.weight"] = torch.zeros(1)
+    with pytest.raises(CheckpointError):
+        m.load_state_dict(bad)
+    bad = dict(sd); bad["logits_head.weight"] = torch.zeros(64, 767)
+    with pytest.raises(CheckpointError):
+        m.load_state_dict(bad)
+    with pytest.raises(Exception):
+        m.audio_cond(torch.zeros(1, 64000))                       # nothing loaded -> loud failure
+
+
+# ----------------------------------------------------------------------------- FLAME + engine surface
+def test_flame_matches_golden_and_oracle():
+    g = gu.load("flame")
+    asset = synthetic.make_flame_asset(0)
+    shape, motion = flame_inputs()
+    for scale in (1.0, 5.0):
+        fm = FLAMEModel(n_shape=300, n_exp=100, scale=scale, no_lmks=True, asset=asset, device=DEV)
+        vae = model("TINY", "fp32").basic_vae
+        for wg in (False, True):
+            v = vae.get_flame_verts(fm, shape.to(DEV), motion.to(DEV), with_global=wg).cpu()
+            key = "verts_scale%g_global%d" % (scale, int(wg))
+            assert v.shape == (6, 5023, 3)
+            np.testing.assert_allclose(v.numpy(), g[key], atol=1e-4 * scale, rtol=0)
+    # shared (expanded) shape row fast path == per-frame shape rows; 3-D shape loops over the batch
+    fm = FLAMEModel(n_shape=300, n_exp=100, scale=1.0, no_lmks=True, asset=asset, device=DEV)
+    m37 = 0.3 * torch.randn(37, 106, generator=torch.Generator().manual_seed(1))
+    sh1 = 0.5 * torch.randn(1, 300, generator=torch.Generator().manual_seed(2))
+    v_shared = vae.get_flame_verts(fm, sh1.to(DEV).expand(37, -1), m37.to(DEV), with_global=True).cpu()
+    ref = get_flame_verts(asset, sh1.expand(37, -1), m37, with_global=True)
+    np.testing.assert_allclose(v_shared.numpy(), ref.numpy(), atol=1e-4, rtol=0)
+    v_rows = vae.get_flame_verts(fm, sh1.repeat(37, 1).to(DEV), m37.to(DEV), with_global=True).cpu()
+    np.testing.assert_allclose(v_rows.numpy(), ref.numpy(), atol=1e-4, rtol=0)
+    v3 = vae.get_flame_verts(fm, sh1.repeat(2, 5, 1).to(DEV), m37[:10].view(2, 5, 106).to(DEV), with_global=True)
+    assert v3.shape == (2, 5, 5023, 3)
+    with pytest.raises(ValueError):
+        vae.get_flame_verts(fm, sh1[0].to(DEV), m37.to(DEV))
+
+
+def test_smooth_motion_matches_scipy():
+    from scipy.signal import savgol_filter
+    m = torch.randn(3, 57, 106, generator=torch.Generator().manual_seed(4))
+    for fix_pose in (False, True):
+        got = smooth_motion(m.to(DEV), clip_length=40, fix_pose=fix_pose).cpu().numpy()
+        ref = savgol_filter(m.numpy(), 5, 2, axis=1)
+        ref[..., 100:103] = savgol_filter(m.numpy()[..., 100:103], 9, 3, axis=1)
+        ref = ref[:, :40]
+        if fix_pose:
+            ref[..., 100:103] = 0
+        ref[..., 104:] = 0
+        np.testing.assert_allclose(got, ref, atol=2e-5, rtol=0)
+    with pytest.raises(ValueError):
+        smooth_motion(m[:, :8].to(DEV))
+    only = ARTAvatarInferEngine.smooth_motion_savgol(m[0].to(DEV)).cpu().numpy()
+    ref = savgol_filter(m[0].numpy(), 5, 2, axis=0)
+    ref[..., 100:103] = savgol_filter(m[0].numpy()[..., 100:103], 9, 3, axis=0)
+    np.testing.assert_allclose(only, ref, atol=2e-5, rtol=0)
+
+
+def test_engine_surface_matches_reference_golden():
+    case = CASES["tiny_style"]
+    g = gu.load("engine_tiny")
+    gv = gu.load("engine_tiny_verts")
+    eng = ARTAvatarInferEngine(load_gaga=False, clip_length=120, device=DEV, precision="fp32",
+                               state_dict=gu.state_dict("TINY"), config=config.TINY.to_reference_json(),
+                               flame_asset=synthetic.make_flame_asset(0), wav2vec=config.TINY.wav2vec, make_output_dir=False)
+    with pytest.raises(AssertionError):
+        eng.set_style_motion(torch.zeros(49, 106))
+    eng.set_style_motion(case.style()[0])
+    out = eng.inference(case.audio()[0])
+    assert tuple(out.shape) == (120, 106) and out.device.type == "cuda"
+    np.testing.assert_allclose(out.cpu().numpy(), g["motion"], atol=1e-3, rtol=0)
+    assert float(out[:, 104:].abs().max()) == 0.0
+    verts = eng.mesh_vertices(out)
+    np.testing.assert_allclose(verts[:3].cpu().numpy(), gv["verts"], atol=1e-3, rtol=0)
+    with pytest.raises(NotImplementedError):
+        eng.rendering(None, out)
