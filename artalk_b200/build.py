@@ -56,7 +56,9 @@ def build(verbose: bool = False, force: bool = False) -> str:
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+        # static cudart (nvcc default); the driver entry point for TMA descriptors is fetched at run time with
+        # cudaGetDriverEntryPoint, so the library also loads on a box without libcuda (CPU tests)
+        cmd = [NVCC, "-shared", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr[-4000:])

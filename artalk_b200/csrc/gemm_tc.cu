@@ -1,8 +1,441 @@
-// placeholder until the tcgen05 kernel lands in this file
+// bf16 tensor-core GEMM for sm_100a:  out = resid + gate * act(A W^T + bias), fp32 accumulation in TMEM.
+//
+//  * operands arrive by TMA (cp.async.bulk.tensor.3d, 128B swizzle) into a multi-stage shared-memory ring;
+//    A is described by a 3-D tensor map (K, rows-in-batch, batch) so the same kernel covers plain matrices,
+//    batched row views, the overlapping-row implicit-GEMM view of the wav2vec conv layers and (tap mode) the
+//    grouped positional conv, with zero fill outside a batch's rows doing the conv padding;
+//  * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BN, K=16 per instruction) with the
+//    accumulator in TMEM; two accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1;
+//  * 4 epilogue warps read their TMEM lane quarter with tcgen05.ld (one output row per thread) and apply
+//    bias / activation / gate / residual before 16-byte global stores;
+//  * persistent: grid = min(tiles, #SMs), tiles are walked N-fastest so an A tile is shared through L2.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+#include <cuda.h>
+#include <cstdio>
+#include <map>
+#include <mutex>
 #include "kernels.cuh"
+
 namespace artalk {
-int launch_gemm_tc(const GemmArgs&, cudaStream_t) {
-  set_last_error("bf16 tcgen05 GEMM not built yet");
-  return AT_EINVAL;
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
+
+struct TcParams {
+  int N;
+  int rpb;                 // rows per batch of the A view (tile rows never cross a batch)
+  int n_batches, tiles_per_batch, n_tiles_n, groups, total_tiles;
+  int num_kb;              // K blocks of 64
+  int tap_mode, tap_pad;   // tap mode: k-block j reads rows shifted by (j - tap_pad), columns of group g
+  int a_group_cols;        // column offset per group in the A view (tap mode)
+  int64_t c_gs; int bias_gs;
+  const float* bias; int act;
+  const void* gate; int gate_dt; RowMap gate_map;
+  const float* resid; RowMap resid_map;
+  float* out32; void* out_act; int out_act_dt; RowMap c_map;
+  int vec_ok;
+  unsigned int* err_flag;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err_flag, int who) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 20000000u) {
+      if (err_flag) atomicExch(err_flag, 0xDEAD0000u | (uint32_t)who);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, 128B swizzle: 8-row groups of 1024 B (SBO), version 1 (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address >> 4
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset = 1024 B
+  d |= (uint64_t)1 << 46;                          // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN> struct TileCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int tile, int& n_idx, int& mt, int& b, int& g) {
+    n_idx = tile % p.n_tiles_n;
+    int rest = tile / p.n_tiles_n;
+    mt = rest % p.tiles_per_batch;
+    rest /= p.tiles_per_batch;
+    b = rest % p.n_batches;
+    g = rest / p.n_batches;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n_idx, mt, b, g;
+        decode(tile, n_idx, mt, b, g);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          if (p.tap_mode) tma_load_3d(sa, &tmA, full_bar(stage), g * p.a_group_cols, mt * BM + kb - p.tap_pad, b);
+          else tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, mt * BM, b);
+          tma_load_3d(sb, &tmW, full_bar(stage), kb * BK, n_idx * BN, g);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(empty_bar(stage));           // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));               // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                      // TMEM lane quarter of this warp
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int n_idx, mt, b, g;
+      decode(tile, n_idx, mt, b, g);
+      const int acc = it & 1;
+      mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 4);
+      tc_fence_after();
+      const int t_in_batch = mt * BM + q * 32 + lane;
+      const bool row_ok = t_in_batch < p.rpb;
+      const int r = b * p.rpb + t_in_batch;
+      const int64_t cg = (int64_t)g * p.c_gs;
+      const int64_t c_off = row_ok ? p.c_map.off(r) + cg : 0;
+      const int64_t g_off = (row_ok && p.gate) ? p.gate_map.off(r) + cg : 0;
+      const int64_t r_off = (row_ok && p.resid) ? p.resid_map.off(r) + cg : 0;
+      const float* bias = p.bias ? p.bias + g * p.bias_gs : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        const int col0 = n_idx * BN + c * 32;
+        if (!row_ok || col0 >= p.N) continue;
+        if (p.vec_ok && col0 + 32 <= p.N) {
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          }
+          if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (p.gate) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float gv[4];
+              if (p.gate_dt == DT_F32) load4(reinterpret_cast<const float*>(p.gate) + g_off + col0 + j, gv);
+              else load4(reinterpret_cast<const bf16*>(p.gate) + g_off + col0 + j, gv);
+              v[j] *= gv[0]; v[j + 1] *= gv[1]; v[j + 2] *= gv[2]; v[j + 3] *= gv[3];
+            }
+          }
+          if (p.resid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float rv[4];
+              load4(p.resid + r_off + col0 + j, rv);
+              v[j] += rv[0]; v[j + 1] += rv[1]; v[j + 2] += rv[2]; v[j + 3] += rv[3];
+            }
+          }
+          if (p.out32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.out32 + c_off + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (p.out_act) {
+            if (p.out_act_dt == DT_F32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + c_off + col0 + j) =
+                    make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_act) + c_off + col0 + j) = pk;
+              }
+            }
+          }
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
+            float t = v[j];
+            if (bias) t += bias[col0 + j];
+            t = apply_act(t, p.act);
+            if (p.gate)
+              t *= (p.gate_dt == DT_F32) ? reinterpret_cast<const float*>(p.gate)[g_off + col0 + j]
+                                         : __bfloat162float(reinterpret_cast<const bf16*>(p.gate)[g_off + col0 + j]);
+            if (p.resid) t += p.resid[r_off + col0 + j];
+            if (p.out32) p.out32[c_off + col0 + j] = t;
+            if (p.out_act) {
+              if (p.out_act_dt == DT_F32) reinterpret_cast<float*>(p.out_act)[c_off + col0 + j] = t;
+              else reinterpret_cast<bf16*>(p.out_act)[c_off + col0 + j] = __float2bfloat16_rn(t);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes,
+                uint32_t b0, uint32_t b1) {
+  EncodeTiledFn enc = get_encode();
+  AT_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u) base=%p", (int)r,
+                   (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_bytes,
+                   (unsigned long long)s2_bytes, b0, b1, base);
+    return AT_ECUDA;
+  }
+  return AT_OK;
+}
+
+unsigned int* g_err_flag = nullptr;
+int g_num_sms = 0;
+
+template <int BN>
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t st) {
+  using Cfg = TileCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  gemm_tc_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmW, p);
+  AT_LAUNCH_CHECK();
+  return AT_OK;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return AT_OK;
+  AT_REQUIRE(g.A && g.W && (g.out32 || g.out_act), "gemm_tc: null operand");
+  AT_REQUIRE(g.K > 0 && g.K % 16 == 0, "gemm_tc: K=%d must be a positive multiple of 16", g.K);
+  AT_REQUIRE(g.ldw % 8 == 0 && g.a_map.rs % 8 == 0 && g.a_map.bs % 8 == 0 && g.a_gs % 8 == 0 && g.w_gs % 8 == 0,
+             "gemm_tc: operand strides must be multiples of 8 elements (16 bytes)");
+  AT_REQUIRE(((uintptr_t)g.A) % 16 == 0 && ((uintptr_t)g.W) % 16 == 0, "gemm_tc: operands must be 16-byte aligned");
+  AT_REQUIRE(g.tap_w == 0 || (g.tap_w == BK && g.a_map.rpb > 0 && g.K % BK == 0), "gemm_tc: tap mode needs tap_w == 64");
+  AT_REQUIRE(g.groups == 1 || g.tap_w > 0, "gemm_tc: groups are only supported in tap mode");
+  if (!g_err_flag) {
+    AT_CUDA(cudaMalloc((void**)&g_err_flag, sizeof(unsigned int)));
+    AT_CUDA(cudaMemset(g_err_flag, 0, sizeof(unsigned int)));
+    int dev = 0;
+    AT_CUDA(cudaGetDevice(&dev));
+    AT_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  TcParams p;
+  p.N = g.N;
+  const bool batched = g.a_map.rpb > 0;
+  p.rpb = batched ? g.a_map.rpb : g.M;
+  p.n_batches = batched ? ceil_div(g.M, g.a_map.rpb) : 1;
+  AT_REQUIRE(!batched || g.M % g.a_map.rpb == 0, "gemm_tc: M must be a multiple of the A view's rows per batch");
+  p.tiles_per_batch = ceil_div(p.rpb, BM);
+  const int BN = g.N >= 256 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : 32;
+  p.n_tiles_n = ceil_div(g.N, BN);
+  p.groups = g.groups;
+  p.total_tiles = p.groups * p.n_batches * p.tiles_per_batch * p.n_tiles_n;
+  p.num_kb = ceil_div(g.K, BK);
+  p.tap_mode = g.tap_w > 0 ? 1 : 0; p.tap_pad = g.tap_pad; p.a_group_cols = (int)g.a_gs;
+  p.c_gs = g.c_gs; p.bias_gs = g.bias_gs; p.bias = g.bias; p.act = g.act;
+  p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
+  p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;
+  p.err_flag = g_err_flag;
+  bool v = (g.c_map.rs % 8 == 0) && (g.c_map.bs % 8 == 0) && (g.c_gs % 8 == 0);
+  if (g.bias) v = v && (((uintptr_t)g.bias) % 16 == 0) && (g.bias_gs % 4 == 0);
+  if (g.gate) v = v && (g.gate_map.rs % 8 == 0) && (g.gate_map.bs % 8 == 0) && (((uintptr_t)g.gate) % 16 == 0);
+  if (g.resid) v = v && (g.resid_map.rs % 4 == 0) && (g.resid_map.bs % 4 == 0) && (((uintptr_t)g.resid) % 16 == 0);
+  if (g.out32) v = v && (((uintptr_t)g.out32) % 16 == 0);
+  if (g.out_act) v = v && (((uintptr_t)g.out_act) % 16 == 0);
+  p.vec_ok = v ? 1 : 0;
+
+  CUtensorMap tmA, tmW;
+  // A view: (K or full row width in tap mode, rows per batch, batches)
+  const uint64_t a_d0 = p.tap_mode ? (uint64_t)g.a_map.rs : (uint64_t)g.K;
+  const uint64_t a_s1 = (uint64_t)g.a_map.rs * 2;
+  const uint64_t a_s2 = batched ? (uint64_t)g.a_map.bs * 2 : (uint64_t)p.rpb * g.a_map.rs * 2;
+  AT_TRY(make_map_3d(&tmA, g.A, a_d0, (uint64_t)p.rpb, (uint64_t)p.n_batches, a_s1, a_s2 ? a_s2 : 16, BK, BM));
+  const uint64_t w_s2 = g.groups > 1 ? (uint64_t)g.w_gs * 2 : (uint64_t)g.N * g.ldw * 2;
+  AT_TRY(make_map_3d(&tmW, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.groups, (uint64_t)g.ldw * 2, w_s2, BK, (uint32_t)BN));
+  switch (BN) {
+    case 256: return launch_bn<256>(tmA, tmW, p, st);
+    case 128: return launch_bn<128>(tmA, tmW, p, st);
+    case 64: return launch_bn<64>(tmA, tmW, p, st);
+    default: return launch_bn<32>(tmA, tmW, p, st);
+  }
+}
+
 }  // namespace artalk

@@ -187,7 +187,7 @@ class BitwiseARModel:
         if self._init_words is None:
             z = torch.zeros(1, self.cfg.chunk_frames, self.cfg.motion_dim, device=self._device)
             self._init_words = self.motion_to_words(z)
-        return self._init_words.expand(batch, -1).contiguous()
+        return self._init_words.repeat(batch, 1)          # fresh copy: ar_chunk updates prev_words in place
 
     def ar_chunk(self, cond: torch.Tensor, style: torch.Tensor, prev_words: torch.Tensor, motion_out: torch.Tensor,
                  words_out=None, logits_out=None, forced_words=None, enc_out=None):

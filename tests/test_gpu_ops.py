@@ -60,7 +60,7 @@ def test_gemm_bias_act(pname, prec, dt, tol, M, N, K, act):
     b = torch.randn(N, generator=g).to(dev())
     out = torch.full((M, N), float("nan"), device=dev())
     run_gemm(prec, A, W, M, N, K, bias=b, act=act, out32=out)
-    ref = ACTS[act](A.float() @ W.float().t() + b)
+    ref = ACTS[act](A.double() @ W.double().t() + b.double()).float()     # fp64: torch fp32 matmul may use TF32
     assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
@@ -84,7 +84,7 @@ def test_gemm_gate_residual_rowmaps(pname, prec, dt, tol):
     gate_ptr_t = ada.view(-1)[off * n_ada + C:]
     run_gemm(prec, A, W, M, C, K, bias=b, gate=gate_ptr_t, gate_map=rowmap(n_new, L * n_ada, n_ada), resid=x, out32=x,
              out_act=xa)
-    ref = x0 + (A.float() @ W.float().t() + b) * gate_view.reshape(M, C).float()
+    ref = (x0.double() + (A.double() @ W.double().t() + b.double()) * gate_view.reshape(M, C).double()).float()
     scale = max(1.0, ref.abs().max().item())
     assert (x - ref).abs().max().item() < tol * scale
     assert (xa.float() - ref).abs().max().item() < (tol + (0 if dt == torch.float32 else 8e-3)) * scale
@@ -103,7 +103,7 @@ def test_conv_as_overlapping_row_gemm(pname, prec, dt, tol, k, s):
     wp = w.permute(0, 2, 1).reshape(Cc, k * Cc).contiguous()
     out = torch.empty(n * L_out, Cc, device=dev())
     run_gemm(prec, x, wp, n * L_out, Cc, k * Cc, a_map=rowmap(L_out, L_in * Cc, s * Cc), bias=b, out32=out)
-    ref = F.conv1d(x.float().transpose(1, 2), w.float(), b, stride=s).transpose(1, 2).reshape(n * L_out, Cc)
+    ref = F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), stride=s).transpose(1, 2).reshape(n * L_out, Cc).float()
     assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
@@ -122,8 +122,8 @@ def test_pos_conv_grouped_tap_gemm(pname, prec, dt, tol):
     run_gemm(prec, A, wp, n * Fr, gw, K * gw, a_map=rowmap(Fr, Fr * H, H), tap_w=gw, tap_pad=K // 2, groups=G, a_gs=gw,
              w_gs=gw * K * gw, c_gs=gw, bias_gs=gw, bias=b, act=1, resid=h.view(-1, H), resid_map=rowmap(0, 0, H),
              out32=out, c_map=rowmap(0, 0, H), ldw=K * gw)
-    pc = F.conv1d(A.float().transpose(1, 2), w.to(dt).float(), b, padding=K // 2, groups=G)[:, :, :-1]
-    ref = (h + F.gelu(pc).transpose(1, 2)).reshape(n * Fr, H)
+    pc = F.conv1d(A.double().transpose(1, 2), w.to(dt).double(), b.double(), padding=K // 2, groups=G)[:, :, :-1]
+    ref = (h.double() + F.gelu(pc).transpose(1, 2)).reshape(n * Fr, H).float()
     assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
@@ -167,7 +167,7 @@ def test_layernorm(cols, act):
     g = torch.Generator(device="cpu").manual_seed(cols)
     x = (3 * torch.randn(333, cols, generator=g) + 1.5).to(dev())
     gam, bet = torch.randn(cols, generator=g).to(dev()), torch.randn(cols, generator=g).to(dev())
-    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 3e-2)):
+    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 8e-3)):
         out = torch.empty(333, cols, device=dev(), dtype=dt)
         _lib.check(_lib.lib().artalk_op_layernorm(x.data_ptr(), out.data_ptr(), _lib.F32 if dt == torch.float32 else _lib.BF16,
                                                   gam.data_ptr(), bet.data_ptr(), 333, cols, 1e-5, act, _lib.stream_ptr(dev())))
@@ -175,4 +175,4 @@ def test_layernorm(cols, act):
         ref = F.layer_norm(x, (cols,), gam, bet, 1e-5)
         if act:
             ref = F.gelu(ref)
-        assert (out.float() - ref).abs().max().item() < tol
+        assert ((out.float() - ref).abs() / (1.0 + ref.abs())).max().item() < tol
