@@ -93,6 +93,9 @@ SYMBOLS = {
                                         C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "artalk_set_savgol_tables": (C.c_int, [C.c_void_p, C.c_void_p]),
     "artalk_smooth_motion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "artalk_launch_count": (C.c_ulonglong, []),
+    "artalk_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "artalk_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "artalk_op_gemm": (C.c_int, [C.POINTER(Gemm), C.c_int, C.c_void_p]),
     "artalk_op_attention": (C.c_int, [C.POINTER(Attn), C.c_void_p]),
     "artalk_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

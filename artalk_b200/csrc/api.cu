@@ -125,6 +125,16 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
   return launch_savgol_post(motion, out, n_clips, n_frames, n_frames_out, 106, fix_pose, zero_tail, (cudaStream_t)stream);
 }
 
+unsigned long long artalk_launch_count(void) { return g_launch_count; }
+int artalk_profile_enable(artalk_engine_t* e, int enable) {
+  AT_REQUIRE(e, "null engine");
+  return e->eng.prof_begin(enable);
+}
+int artalk_profile_read(artalk_engine_t* e, double* host_out8, void* stream) {
+  AT_REQUIRE(e && host_out8, "null argument");
+  return e->eng.prof_read(host_out8, (cudaStream_t)stream);
+}
+
 int artalk_op_gemm(const artalk_gemm_t* a, int precision, void* stream) {
   AT_REQUIRE(a, "null gemm");
   GemmArgs g = gemm_args();

@@ -24,7 +24,12 @@ void set_last_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
-#define AT_LAUNCH_CHECK() AT_CUDA(cudaGetLastError())
+extern unsigned long long g_launch_count;      // kernels launched by this library (bench.py's gpu_launches)
+#define AT_LAUNCH_CHECK()                 \
+  do {                                    \
+    ++::artalk::g_launch_count;           \
+    AT_CUDA(cudaGetLastError());          \
+  } while (0)
 
 #define AT_REQUIRE(cond, ...)                                                                \
   do {                                                                                       \

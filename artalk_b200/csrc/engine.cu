@@ -177,8 +177,51 @@ void* Engine::ws_alloc(size_t bytes) {
   type var = (type)ws_alloc(bytes);                       \
   if (!var) return AT_ENOMEM
 
-int Engine::gemm(const GemmArgs& g, cudaStream_t st) const {
-  return cfg.precision == 0 ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st);
+unsigned long long g_launch_count = 0;
+
+int Engine::prof_begin(int enable) {
+  prof = enable != 0;
+  prof_flops.clear(); prof_cls.clear();
+  if (prof && prof_ev.empty()) {
+    prof_ev.resize(2 * 8192);
+    for (auto& e : prof_ev) AT_CUDA(cudaEventCreate(&e));
+  }
+  return AT_OK;
+}
+
+// out8 = {gemm launches, gemm ms, gemm flops, attn launches, attn ms, attn flops, dropped, 0}
+int Engine::prof_read(double* out, cudaStream_t st) {
+  AT_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < 8; ++i) out[i] = 0.0;
+  for (size_t i = 0; i < prof_cls.size(); ++i) {
+    float ms = 0.f;
+    AT_CUDA(cudaEventElapsedTime(&ms, prof_ev[2 * i], prof_ev[2 * i + 1]));
+    int c = prof_cls[i] * 3;
+    out[c] += 1.0; out[c + 1] += ms; out[c + 2] += prof_flops[i];
+  }
+  return AT_OK;
+}
+
+#define PROF_WRAP(cls, flops, call)                                             \
+  do {                                                                          \
+    size_t _i = prof_cls.size();                                                \
+    bool _on = prof && 2 * _i + 1 < prof_ev.size();                             \
+    if (_on) AT_CUDA(cudaEventRecord(prof_ev[2 * _i], st));                     \
+    AT_TRY(call);                                                               \
+    if (_on) {                                                                  \
+      AT_CUDA(cudaEventRecord(prof_ev[2 * _i + 1], st));                        \
+      prof_cls.push_back(cls); prof_flops.push_back(flops);                     \
+    }                                                                           \
+    return AT_OK;                                                               \
+  } while (0)
+
+int Engine::gemm(const GemmArgs& g, cudaStream_t st) {
+  PROF_WRAP(0, 2.0 * g.M * g.N * g.K * g.groups, cfg.precision == 0 ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st));
+}
+
+int Engine::attention(const AttnArgs& a, cudaStream_t st) {
+  double keys = (a.split > 0) ? 0.5 * (a.split + a.lk) : a.lk;     // rows < split see `split` keys, the rest see lk
+  PROF_WRAP(1, 4.0 * a.n_seq * a.n_heads * a.head_dim * a.lq * keys, launch_attention(a, st));
 }
 
 // ------------------------------------------------------------------ wav2vec2
@@ -277,7 +320,7 @@ int Engine::audio_encode_sub(const float* audio, int n, float* cond, cudaStream_
     a.n_seq = n; a.n_heads = c.w2v_heads; a.head_dim = H / c.w2v_heads; a.lq = F; a.lk = F;
     a.q_ss = a.k_ss = a.v_ss = (int64_t)F * 3 * H; a.q_rs = a.k_rs = a.v_rs = 3 * H;
     a.o_ss = (int64_t)F * H; a.o_rs = H; a.scale = att_scale; a.split = 0;
-    AT_TRY(launch_attention(a, st));
+    AT_TRY(attention(a, st));
     g = gemm_args();
     g.A = bufB; g.a_map = plain_rows(H); g.W = getw(S("w2v.l%d.out.w", l)); g.ldw = H; g.M = M; g.N = H; g.K = H;
     g.bias = get<float>(S("w2v.l%d.out.b", l)); g.resid = h; g.resid_map = plain_rows(H); g.out32 = h; g.c_map = plain_rows(H);
@@ -331,7 +374,7 @@ int Engine::style_encode(const float* style_motion, int n, float* style_out, cud
     a.head_dim = SD / c.style_heads; a.lq = SL; a.lk = SL; a.q_ss = a.k_ss = a.v_ss = (int64_t)SL * 3 * SD;
     a.q_rs = a.k_rs = a.v_rs = 3 * SD; a.o_ss = (int64_t)SL * SD; a.o_rs = SD;
     a.scale = 1.0f / sqrtf((float)a.head_dim); a.split = 0;
-    AT_TRY(launch_attention(a, st));
+    AT_TRY(attention(a, st));
     g = gemm_args();
     g.A = o; g.a_map = plain_rows(SD); g.W = getw(S("style.l%d.out.w", l)); g.ldw = SD; g.M = M; g.N = SD; g.K = SD;
     g.bias = get<float>(S("style.l%d.out.b", l)); g.resid = x; g.resid_map = plain_rows(SD); g.out32 = t; g.c_map = plain_rows(SD);
@@ -382,7 +425,7 @@ int Engine::vae_stack(const char* side, int n, int rows, int split, float* x, vo
     a.q_ss = a.k_ss = a.v_ss = (int64_t)rows * 3 * VH; a.q_rs = a.k_rs = a.v_rs = 3 * VH; a.o_ss = (int64_t)rows * VH; a.o_rs = VH;
     a.scale = 1.0f / sqrtf((float)VH);            // quirk 2: hidden_dim ** -0.5
     a.split = split;
-    AT_TRY(launch_attention(a, st));
+    AT_TRY(attention(a, st));
     g = gemm_args();
     g.A = nv; g.a_map = plain_rows(VH); g.W = getw(S("vae.%s.l%d.out.w", side, l)); g.ldw = VH; g.M = M; g.N = VH; g.K = VH;
     g.bias = get<float>(S("vae.%s.l%d.out.b", side, l)); g.resid = x; g.resid_map = plain_rows(VH); g.out32 = x; g.c_map = plain_rows(VH);
@@ -529,7 +572,7 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
       a.lq = n_new; a.lk = P + off + n_new;          // prev chunk + every current token of scale <= p
       a.q_ss = (int64_t)n_new * C; a.q_rs = C; a.k_ss = a.v_ss = (int64_t)KV * C; a.k_rs = a.v_rs = C;
       a.o_ss = (int64_t)n_new * C; a.o_rs = C; a.scale = 1.0f; a.split = 0;
-      AT_TRY(launch_attention(a, st));
+      AT_TRY(attention(a, st));
       g = gemm_args();
       g.A = o; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.proj.w", l)); g.ldw = C; g.M = M; g.N = C; g.K = C;
       g.bias = get<float>(S("ar.l%d.proj.b", l)); g.gate = ada_l; g.gate_dt = adt; g.gate_map = ada_map;       // gamma1

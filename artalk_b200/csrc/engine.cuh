@@ -46,7 +46,13 @@ struct Engine {
   void* ws_alloc(size_t bytes);
   void ws_reset() { ws_off = 0; }
 
-  int gemm(const GemmArgs& g, cudaStream_t st) const;
+  int gemm(const GemmArgs& g, cudaStream_t st);
+  int attention(const AttnArgs& a, cudaStream_t st);
+  // optional CUDA-event instrumentation of the GEMM / attention launches (bench.py roofline pass)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev; std::vector<double> prof_flops; std::vector<int> prof_cls;
+  int prof_begin(int enable);
+  int prof_read(double* out8, cudaStream_t st);
 
   size_t audio_ws_per_chunk() const;
   int audio_encode(const float* audio, int n_chunks, float* cond, cudaStream_t st);

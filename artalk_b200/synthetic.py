@@ -24,7 +24,7 @@ from .config import ModelConfig
 
 # init kinds -----------------------------------------------------------------
 LINEAR_W, BIAS, LN_W, LN_B, EMBED, NULL_STYLE, SCALE_MUL, STATS_MEAN, STATS_STD, \
-    PE, ATTN_MASK_AR, LVL_IDX, ATTN_MASK_VAE, POSCONV_G, POSCONV_V, CONV0_W, UNIT = range(17)
+    PE, ATTN_MASK_AR, LVL_IDX, ATTN_MASK_VAE, POSCONV_G, POSCONV_V, CONV0_W, UNIT, OUT_W = range(18)
 
 
 def state_dict_spec(cfg: ModelConfig) -> "OrderedDict[str, Tuple[tuple, torch.dtype, int]]":
@@ -39,7 +39,9 @@ def state_dict_spec(cfg: ModelConfig) -> "OrderedDict[str, Tuple[tuple, torch.dt
         s[name] = (tuple(shape), dtype, kind)
 
     def linear(prefix, out_f, in_f, bias=True):
-        add(prefix + ".weight", (out_f, in_f), LINEAR_W)
+        # decoder out_mapping: small init like the reference's xavier(gain=0.05) (bitwise_vae.py:168-169) so that the
+        # decoded (normalised) motion is O(1) and the absolute parity tolerances on FLAME codes are meaningful
+        add(prefix + ".weight", (out_f, in_f), OUT_W if prefix.endswith("decoder.out_mapping") else LINEAR_W)
         if bias:
             add(prefix + ".bias", (out_f,), BIAS)
 
@@ -153,6 +155,8 @@ def _make(name: str, shape, dtype, kind: int, cfg: ModelConfig, seed: int) -> to
         for d in shape[1:]:
             fan_in *= d
         return rn(*shape) * (1.0 / math.sqrt(fan_in))
+    if kind == OUT_W:
+        return rn(*shape) * (0.15 / math.sqrt(shape[1]))
     if kind == CONV0_W:
         return rn(*shape) * math.sqrt(2.0 / shape[-1])
     if kind == BIAS:

@@ -118,6 +118,15 @@ int artalk_set_savgol_tables(const float* host_h5, const float* host_h9);
 int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_frames, int n_frames_out, int fix_pose,
                          int zero_tail, void* stream);
 
+/* --- measurement hooks (bench.py) ---
+ * artalk_launch_count: kernels launched by this library in this process so far.
+ * artalk_profile_enable(e, 1): bracket every GEMM / attention launch of the engine with CUDA events on the launching
+ * stream; artalk_profile_read synchronises and fills host_out8 = {gemm launches, gemm ms, gemm flops, attention
+ * launches, attention ms, attention flops, 0, 0} accumulated since the last enable call. */
+unsigned long long artalk_launch_count(void);
+int artalk_profile_enable(artalk_engine_t* e, int enable);
+int artalk_profile_read(artalk_engine_t* e, double* host_out8, void* stream);
+
 /* ---------------- operator-level entry points (unit parity tests of single kernels) ---------------- */
 typedef struct artalk_rowmap { int rpb; int64_t bs, rs; } artalk_rowmap_t;
 typedef struct artalk_gemm {
