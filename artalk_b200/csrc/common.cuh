@@ -67,6 +67,13 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   float inner = k0 * (x + k1 * x * x * x);
   return 0.5f * x * (1.0f + tanhf(inner));
 }
+// bf16-path variant: hardware tanh.approx (rel. error ~2^-11, below bf16 rounding of the result)
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x), t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  return 0.5f * x * (1.0f + t);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {

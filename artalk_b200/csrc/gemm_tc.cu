@@ -6,10 +6,10 @@
 //    grouped positional conv, with zero fill outside a batch's rows doing the conv padding;
 //  * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BN, K=16 per instruction) with the
 //    accumulator in TMEM; two accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1;
-//  * 4 epilogue warps read their TMEM lane quarter with tcgen05.ld (one output row per thread) and apply
+//  * 8 epilogue warps read their TMEM lane quarter with tcgen05.ld (one output row per thread) and apply
 //    bias / activation / gate / residual before 16-byte global stores;
 //  * persistent: grid = min(tiles, #SMs), tiles are walked N-fastest so an A tile is shared through L2.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue (lane quarter x column half).
 #include <cuda.h>
 #include <cstdio>
 #include <map>
@@ -131,7 +131,7 @@ template <int BN> struct TileCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -155,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -219,8 +219,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp - 4;                      // TMEM lane quarter of this warp
+    // ===================== epilogue: 8 warps, warp -> (TMEM lane quarter, column half) =====================
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int n_idx, mt, b, g;
@@ -237,23 +237,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t r_off = (row_ok && p.resid) ? p.resid_map.off(r) + cg : 0;
       const float* bias = p.bias ? p.bias + g * p.bias_gs : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
         const int col0 = n_idx * BN + c * 32;
         if (!row_ok || col0 >= p.N) continue;
-        if (p.vec_ok && col0 + 32 <= p.N) {
-          if (bias) {
+        const bool full = p.vec_ok && (col0 + 32 <= p.N);
+        // ---- bias
+        if (bias) {
+          if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
               v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
             }
-          }
-          if (p.act != ACT_NONE) {
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
           }
+        }
+        // ---- activation (switch hoisted out of the element loop; fast-math variants: outputs are rounded to bf16)
+        switch (p.act) {
+          case ACT_GELU_ERF:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            break;
+          case ACT_GELU_TANH:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+            break;
+          case ACT_LEAKY02:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+            break;
+          case ACT_SILU:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+            break;
+          default: break;
+        }
+        if (full) {
           if (p.gate) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -295,18 +318,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
-            float t = v[j];
-            if (bias) t += bias[col0 + j];
-            t = apply_act(t, p.act);
-            if (p.gate)
-              t *= (p.gate_dt == DT_F32) ? reinterpret_cast<const float*>(p.gate)[g_off + col0 + j]
-                                         : __bfloat162float(reinterpret_cast<const bf16*>(p.gate)[g_off + col0 + j]);
-            if (p.resid) t += p.resid[r_off + col0 + j];
-            if (p.out32) p.out32[c_off + col0 + j] = t;
-            if (p.out_act) {
-              if (p.out_act_dt == DT_F32) reinterpret_cast<float*>(p.out_act)[c_off + col0 + j] = t;
-              else reinterpret_cast<bf16*>(p.out_act)[c_off + col0 + j] = __float2bfloat16_rn(t);
+          // ragged / unaligned tail: fully unrolled with compile-time indices so v[] stays in registers
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.N) {
+              float t = v[j];
+              if (p.gate)
+                t *= (p.gate_dt == DT_F32) ? reinterpret_cast<const float*>(p.gate)[g_off + col0 + j]
+                                           : __bfloat162float(reinterpret_cast<const bf16*>(p.gate)[g_off + col0 + j]);
+              if (p.resid) t += p.resid[r_off + col0 + j];
+              if (p.out32) p.out32[c_off + col0 + j] = t;
+              if (p.out_act) {
+                if (p.out_act_dt == DT_F32) reinterpret_cast<float*>(p.out_act)[c_off + col0 + j] = t;
+                else reinterpret_cast<bf16*>(p.out_act)[c_off + col0 + j] = __float2bfloat16_rn(t);
+              }
             }
           }
         }
@@ -374,7 +399,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p,
     attr_set = true;
   }
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  gemm_tc_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmW, p);
+  gemm_tc_kernel<BN><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tmA, tmW, p);
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

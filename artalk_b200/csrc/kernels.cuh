@@ -70,7 +70,10 @@ struct AttnArgs {
   float scale;
   int split;                          // >0: query rows < split only see keys < split (bitwise_vae.py:67-76)
 };
+// dispatch: bf16 / head_dim 64 / <= 384 keys -> tcgen05 kernel (attention_tc.cu), otherwise the fp32-arithmetic SIMT kernel
 int launch_attention(const AttnArgs& a, cudaStream_t st);
+bool attention_tc_supported(const AttnArgs& a);
+int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 // AR q/k/v post-processing (app/transformer.py:71-74): per-head L2 normalise q (x exp(min(scale_mul, ln100))) and k,
 // q -> qbuf [M, C]; k,v -> cache rows given by kv_map. qkv: [M, 3C] (q | k | v), or [M, 2C] (k | v) when has_q = 0.
 int launch_qkv_norm_scatter(const void* qkv, int dt, int64_t qkv_rs, int has_q, const float* head_scale, void* qbuf,

@@ -200,7 +200,11 @@ class BitwiseARModel:
 
     # ---- app/models.py:62-121 -------------------------------------------------------------------------
     @torch.no_grad()
-    def inference(self, batch, with_gtmotion=False, trace: Optional[dict] = None, teacher_words: Optional[torch.Tensor] = None):
+    def inference(self, batch, with_gtmotion=False, trace: Optional[dict] = None, teacher_words: Optional[torch.Tensor] = None,
+                  teacher_prev_words: Optional[torch.Tensor] = None):
+        """``trace`` (dict) collects per-chunk intermediates; ``teacher_words`` / ``teacher_prev_words`` (B, n_chunks, 181)
+        int32 force the AR bits fed to the next scale + decoder and the re-encoded bits carried to the next chunk
+        (parity tests: one flipped bit must not cascade through the recurrence)."""
         cfg = self.cfg
         audio = batch["audio"]
         if audio.dim() != 2:
@@ -246,6 +250,8 @@ class BitwiseARModel:
                 if tr is not None:
                     trace["logits"][b0:b1, c].copy_(tr["logits"]); trace["words"][b0:b1, c].copy_(tr["words"])
                     trace["prev_words"][b0:b1, c].copy_(prev_words); trace["enc_out"][b0:b1, c].copy_(tr["enc"])
+                if teacher_prev_words is not None:
+                    prev_words.copy_(teacher_prev_words[b0:b1, c].to(self._device, torch.int32))
         pred_motions = motion.view(B, n_chunks * T, cfg.motion_dim)[:, :seq_length]
         if with_gtmotion:
             min_length = min(batch["motion"].shape[1], pred_motions.shape[1])
