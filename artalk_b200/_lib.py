@@ -82,6 +82,7 @@ SYMBOLS = {
     "artalk_finalize": (C.c_int, [C.c_void_p]),
     "artalk_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_size_t]),
     "artalk_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "artalk_enable_graphs": (C.c_int, [C.c_void_p, C.c_int]),
     "artalk_audio_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "artalk_style_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "artalk_motion_to_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -94,6 +95,8 @@ SYMBOLS = {
     "artalk_set_savgol_tables": (C.c_int, [C.c_void_p, C.c_void_p]),
     "artalk_smooth_motion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "artalk_launch_count": (C.c_ulonglong, []),
+    "artalk_trace_begin": (C.c_int, [C.c_void_p]),
+    "artalk_trace_end": (C.c_long, [C.c_char_p, C.c_long, C.c_void_p]),
     "artalk_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "artalk_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "artalk_op_gemm": (C.c_int, [C.POINTER(Gemm), C.c_int, C.c_void_p]),

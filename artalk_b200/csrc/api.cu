@@ -6,7 +6,7 @@
 
 using namespace artalk;
 
-namespace artalk { const char* last_error(); }
+namespace artalk { const char* last_error(); int trace_begin(cudaStream_t); long trace_end(char*, long, cudaStream_t); }
 
 struct artalk_engine { Engine eng; };
 
@@ -30,6 +30,7 @@ int artalk_create(const artalk_config_t* cfg, artalk_engine_t** out) {
 
 int artalk_destroy(artalk_engine_t* e) {
   if (!e) return AT_OK;
+  e->eng.drop_graphs();
   if (e->eng.ws) cudaFree(e->eng.ws);
   delete e;
   return AT_OK;
@@ -49,6 +50,12 @@ int artalk_set_workspace_limit(artalk_engine_t* e, size_t bytes) {
   return AT_OK;
 }
 size_t artalk_workspace_bytes(const artalk_engine_t* e) { return e ? e->eng.ws_cap : 0; }
+int artalk_enable_graphs(artalk_engine_t* e, int enable) {
+  AT_REQUIRE(e, "null engine");
+  if (!enable) e->eng.drop_graphs();
+  e->eng.use_graphs = enable != 0;
+  return AT_OK;
+}
 
 int artalk_audio_encode(artalk_engine_t* e, const float* audio, int n_chunks, float* cond, void* stream) {
   AT_REQUIRE(e && audio && cond && n_chunks >= 0, "artalk_audio_encode: bad argument");
@@ -126,6 +133,8 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
 }
 
 unsigned long long artalk_launch_count(void) { return g_launch_count; }
+int artalk_trace_begin(void* stream) { return trace_begin((cudaStream_t)stream); }
+long artalk_trace_end(char* host_buf, long cap, void* stream) { return trace_end(host_buf, cap, (cudaStream_t)stream); }
 int artalk_profile_enable(artalk_engine_t* e, int enable) {
   AT_REQUIRE(e, "null engine");
   return e->eng.prof_begin(enable);

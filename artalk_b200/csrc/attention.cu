@@ -125,6 +125,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   AT_REQUIRE(a.head_dim == 64 || a.head_dim == 32, "attention: head_dim %d", a.head_dim);
   AT_REQUIRE(a.lk > 0 && a.k_rs % 4 == 0 && a.v_rs % 4 == 0 && a.k_ss % 4 == 0 && a.v_ss % 4 == 0,
              "attention: key/value strides must be multiples of 4");
+  g_trace_dims[0] = a.n_seq * a.n_heads; g_trace_dims[1] = a.lq; g_trace_dims[2] = a.lk;
   dim3 grid(ceil_div(a.lq, WARPS * RPW), a.n_heads, a.n_seq);
   if (a.dt == DT_F32) {
     if (a.head_dim == 64) attn_kernel<float, 64><<<grid, WARPS * 32, 0, st>>>(a);

@@ -348,6 +348,7 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   AT_TRY(make_map(&tmV, a.v, wq, (uint64_t)a.lk, (uint64_t)a.n_seq, (uint64_t)a.v_rs * 2, ss(a.v_ss, a.v_rs, a.lk)));
   const size_t smem = (size_t)2 * CHUNK_BYTES * (1 + 2 * p.n_kchunks) + 1024 + 256;
   const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
+  g_trace_dims[0] = a.n_seq * a.n_heads; g_trace_dims[1] = a.lq; g_trace_dims[2] = a.lk;
   attn_tc_kernel<<<grid, 256, smem, st>>>(tmQ, tmK, tmV, p);
   AT_LAUNCH_CHECK();
   return AT_OK;

@@ -25,10 +25,16 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 extern unsigned long long g_launch_count;      // kernels launched by this library (bench.py's gpu_launches)
-#define AT_LAUNCH_CHECK()                 \
-  do {                                    \
-    ++::artalk::g_launch_count;           \
-    AT_CUDA(cudaGetLastError());          \
+// optional launch trace (artalk_trace_begin/end): one CUDA event after every launch on the launching stream `st`;
+// the time between consecutive events (kernel + any idle gap before it) is attributed to the launching function.
+extern bool g_trace_on;
+extern int g_trace_dims[3];              // set by launchers that want their problem size in the trace (GEMM, attention)
+void trace_event(const char* func, cudaStream_t st);
+#define AT_LAUNCH_CHECK()                                         \
+  do {                                                            \
+    ++::artalk::g_launch_count;                                   \
+    if (::artalk::g_trace_on) ::artalk::trace_event(__func__, st); \
+    AT_CUDA(cudaGetLastError());                                  \
   } while (0)
 
 #define AT_REQUIRE(cond, ...)                                                                \

@@ -179,6 +179,51 @@ void* Engine::ws_alloc(size_t bytes) {
 
 unsigned long long g_launch_count = 0;
 
+// ------------------------------------------------------------------ launch trace
+bool g_trace_on = false;
+int g_trace_dims[3] = {0, 0, 0};
+struct TraceRec { const char* func; int d[3]; cudaEvent_t ev; };
+static std::vector<TraceRec> g_trace;
+static std::vector<cudaEvent_t> g_trace_pool;
+
+void trace_event(const char* func, cudaStream_t st) {
+  if (g_trace.size() >= g_trace_pool.size()) return;
+  TraceRec r;
+  r.func = func; r.d[0] = g_trace_dims[0]; r.d[1] = g_trace_dims[1]; r.d[2] = g_trace_dims[2];
+  r.ev = g_trace_pool[g_trace.size()];
+  g_trace_dims[0] = g_trace_dims[1] = g_trace_dims[2] = 0;
+  if (cudaEventRecord(r.ev, st) == cudaSuccess) g_trace.push_back(r);
+}
+
+int trace_begin(cudaStream_t st) {
+  if (g_trace_pool.empty()) {
+    g_trace_pool.resize(16384);
+    for (auto& e : g_trace_pool) AT_CUDA(cudaEventCreate(&e));
+  }
+  g_trace.clear();
+  g_trace_on = true;
+  trace_event("begin", st);
+  return AT_OK;
+}
+
+// writes "func,d0,d1,d2,microseconds\n" lines; returns the number of bytes written (or needed if larger than cap)
+long trace_end(char* buf, long cap, cudaStream_t st) {
+  g_trace_on = false;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  long off = 0;
+  for (size_t i = 1; i < g_trace.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_trace[i - 1].ev, g_trace[i].ev);
+    char line[160];
+    int n = snprintf(line, sizeof(line), "%s,%d,%d,%d,%.2f\n", g_trace[i].func, g_trace[i].d[0], g_trace[i].d[1], g_trace[i].d[2],
+                     ms * 1000.0f);
+    if (off + n < cap) memcpy(buf + off, line, n);
+    off += n;
+  }
+  if (off < cap) buf[off] = 0;
+  return off;
+}
+
 int Engine::prof_begin(int enable) {
   prof = enable != 0;
   prof_flops.clear(); prof_cls.clear();
@@ -502,6 +547,9 @@ int Engine::vae_encode_bits(const float* motion, int n, uint32_t* words_out, flo
 }
 
 // ------------------------------------------------------------------ one 100-frame chunk of the AR recurrence
+// The chunk body only reads/writes fixed workspace addresses, so after one eager warm-up per (clips, teacher forcing)
+// it is captured into a CUDA graph and replayed: ~700 launches per chunk become one graph launch (launch gaps dominate
+// the small GEMMs of the recurrence, and batch-1 latency). Inputs/outputs are staged with small D2D copies.
 int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* style, uint32_t* prev_words, float* motion_out,
                      uint32_t* words_out, float* logits_out, const uint32_t* forced_words, float* enc_out, cudaStream_t st) {
   AT_REQUIRE(finalized, "engine not finalized");
@@ -509,15 +557,105 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
   const EngineConfig& c = cfg;
   const int adt = act_dt(), C = c.embed_dim, D = c.cond_dim, NL = c.ar_depth;
   const size_t s = dt_size(adt);
-  const int n_ada = NL * 6 * C + 2 * C, P = L, KV = P + L, Tm = T;
+  const int n_ada = NL * 6 * C + 2 * C, KV = 2 * L, Tm = T;
   const int64_t BL = (int64_t)B * L;
   size_t need = (size_t)BL * D * s + (size_t)BL * n_ada * s + (size_t)BL * C * s + (size_t)BL * NL * 2 * C * s +
                 2 * (size_t)NL * B * KV * C * s + (size_t)B * Tm * C * (4 + 3 * s) + (size_t)B * Tm * 4 * C * s +
-                (size_t)BL * 2 * c.code_dim * 4 + (size_t)BL * 4 +
+                (size_t)BL * 2 * c.code_dim * 4 + (size_t)BL * 4 * 3 + (size_t)B * C * 4 +
+                (size_t)B * Tm * (c.motion_dim + c.code_dim) * 4 +
                 (size_t)B * 2 * Tm * (c.code_dim * s + c.vae_hidden * (4 + s) + c.vae_hidden * s * 4 + c.vae_hidden * s * 3 / 2) +
                 (size_t)B * Tm * (128 * s + c.code_dim * 4) + (4 << 20);
   AT_TRY(ws_reserve(need, st));
+  // staging buffers (fixed offsets at the head of the workspace)
   WS(scond, char*, (size_t)BL * D * s);
+  WS(style_ws, float*, (size_t)B * C * 4);
+  WS(prev_ws, uint32_t*, (size_t)BL * 4);
+  WS(forced_ws, uint32_t*, (size_t)BL * 4);
+  WS(words_ws, uint32_t*, (size_t)BL * 4);
+  WS(logits_ws, float*, (size_t)BL * 2 * c.code_dim * 4);
+  WS(motion_ws, float*, (size_t)B * Tm * c.motion_dim * 4);
+  WS(enc_ws, float*, (size_t)B * Tm * c.code_dim * 4);
+  const size_t body_mark = ws_off;
+  AT_TRY(launch_act_cast(cond, batched_rows(L, cond_cs, D), scond, adt, (int)BL, D, ACT_SILU, st));
+  AT_CUDA(cudaMemcpyAsync(style_ws, style, (size_t)B * C * 4, cudaMemcpyDeviceToDevice, st));
+  AT_CUDA(cudaMemcpyAsync(prev_ws, prev_words, (size_t)BL * 4, cudaMemcpyDeviceToDevice, st));
+  if (forced_words) AT_CUDA(cudaMemcpyAsync(forced_ws, forced_words, (size_t)BL * 4, cudaMemcpyDeviceToDevice, st));
+
+  const bool can_graph = use_graphs && !prof && !g_trace_on;
+  const int key = B * 2 + (forced_words ? 1 : 0);
+  bool launched = false;
+  if (can_graph) {
+    auto it = graphs.find(key);
+    if (it != graphs.end() && it->second.ws_base != ws) {          // workspace was re-allocated: addresses are stale
+      if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+      graphs.erase(it);
+      it = graphs.end();
+    }
+    if (it == graphs.end()) {
+      GraphEntry ge; ge.exec = nullptr; ge.ws_base = ws; ge.warm = 0; ge.n_launches = 0;
+      it = graphs.insert(std::make_pair(key, ge)).first;
+    }
+    GraphEntry& ge = it->second;
+    // the caller's stream may be the legacy default stream, which cannot be captured: capture and replay on an
+    // internal stream that is fenced against the caller's stream with events
+    if (!gstream) {
+      AT_CUDA(cudaStreamCreateWithFlags(&gstream, cudaStreamNonBlocking));
+      AT_CUDA(cudaEventCreateWithFlags(&gev_in, cudaEventDisableTiming));
+      AT_CUDA(cudaEventCreateWithFlags(&gev_out, cudaEventDisableTiming));
+    }
+    if (!ge.exec && ge.warm >= 1) {
+      // second call for this key: capture the body
+      cudaGraph_t graph = nullptr;
+      AT_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));
+      int rc = ar_chunk_body(B, scond, style_ws, prev_ws, motion_ws, words_ws, logits_ws, forced_words ? forced_ws : nullptr, enc_ws,
+                             gstream);
+      cudaError_t ce = cudaStreamEndCapture(gstream, &graph);
+      ws_off = body_mark;
+      if (rc != AT_OK || ce != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        use_graphs = false;                                          // fall back to eager launches for good
+        if (rc != AT_OK) return rc;
+      } else {
+        cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); ge.exec = nullptr; use_graphs = false; }
+      }
+    }
+    if (ge.exec) {
+      AT_CUDA(cudaEventRecord(gev_in, st));
+      AT_CUDA(cudaStreamWaitEvent(gstream, gev_in, 0));
+      AT_CUDA(cudaGraphLaunch(ge.exec, gstream));
+      AT_CUDA(cudaEventRecord(gev_out, gstream));
+      AT_CUDA(cudaStreamWaitEvent(st, gev_out, 0));
+      g_launch_count += ge.n_launches;
+      launched = true;
+    } else if (use_graphs) {
+      unsigned long long l0 = g_launch_count;
+      AT_TRY(ar_chunk_body(B, scond, style_ws, prev_ws, motion_ws, words_ws, logits_ws, forced_words ? forced_ws : nullptr, enc_ws, st));
+      ge.n_launches = g_launch_count - l0;
+      ge.warm++;
+      launched = true;
+    }
+  }
+  if (!launched)
+    AT_TRY(ar_chunk_body(B, scond, style_ws, prev_ws, motion_ws, words_ws, logits_ws, forced_words ? forced_ws : nullptr, enc_ws, st));
+  AT_CUDA(cudaMemcpyAsync(motion_out, motion_ws, (size_t)B * Tm * c.motion_dim * 4, cudaMemcpyDeviceToDevice, st));
+  AT_CUDA(cudaMemcpyAsync(prev_words, prev_ws, (size_t)BL * 4, cudaMemcpyDeviceToDevice, st));
+  if (words_out) AT_CUDA(cudaMemcpyAsync(words_out, words_ws, (size_t)BL * 4, cudaMemcpyDeviceToDevice, st));
+  if (logits_out) AT_CUDA(cudaMemcpyAsync(logits_out, logits_ws, (size_t)BL * 2 * c.code_dim * 4, cudaMemcpyDeviceToDevice, st));
+  if (enc_out) AT_CUDA(cudaMemcpyAsync(enc_out, enc_ws, (size_t)B * Tm * c.code_dim * 4, cudaMemcpyDeviceToDevice, st));
+  return AT_OK;
+}
+
+// all pointer arguments live in the workspace (see ar_chunk); allocations below are a deterministic function of B
+int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t* prev_words, float* motion_out, uint32_t* words,
+                          float* logits, const uint32_t* forced_words, float* enc_out, cudaStream_t st) {
+  const EngineConfig& c = cfg;
+  const int adt = act_dt(), C = c.embed_dim, D = c.cond_dim, NL = c.ar_depth;
+  const size_t s = dt_size(adt);
+  const int n_ada = NL * 6 * C + 2 * C, P = L, KV = P + L, Tm = T;
+  const int64_t BL = (int64_t)B * L;
   WS(ada, char*, (size_t)BL * n_ada * s);
   WS(prev_tok, char*, (size_t)BL * C * s);
   WS(kvtmp, char*, (size_t)BL * NL * 2 * C * s);            // prev K|V of all layers; later reused as per-step qkv
@@ -528,13 +666,8 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
   WS(qbuf, char*, (size_t)B * Tm * C * s);
   WS(o, char*, (size_t)B * Tm * C * s);
   WS(f, char*, (size_t)B * Tm * 4 * C * s);
-  float* logits = logits_out;
-  if (!logits) { logits = (float*)ws_alloc((size_t)BL * 2 * c.code_dim * 4); if (!logits) return AT_ENOMEM; }
-  uint32_t* words = words_out;
-  if (!words) { words = (uint32_t*)ws_alloc((size_t)BL * 4); if (!words) return AT_ENOMEM; }
 
   // AdaLN parameters of every block + head for all 181 tokens, once per chunk (audio-only)
-  AT_TRY(launch_act_cast(cond, batched_rows(L, cond_cs, D), scond, adt, (int)BL, D, ACT_SILU, st));
   GemmArgs g = gemm_args();
   g.A = scond; g.a_map = plain_rows(D); g.W = getw("ar.ada.w"); g.ldw = D; g.M = (int)BL; g.N = n_ada; g.K = D;
   g.bias = get<float>("ar.ada.b"); g.out_act = ada; g.out_act_dt = adt; g.c_map = plain_rows(n_ada);

@@ -64,6 +64,17 @@ struct Engine {
   int ar_chunk(int n_clips, const float* cond, int64_t cond_cs, const float* style, uint32_t* prev_words,
                float* motion_out, uint32_t* words_out, float* logits_out, const uint32_t* forced_words,
                float* enc_out, cudaStream_t st);
+  int ar_chunk_body(int n_clips, const char* scond, const float* style, uint32_t* prev_words, float* motion_out,
+                    uint32_t* words, float* logits, const uint32_t* forced_words, float* enc_out, cudaStream_t st);
+  // CUDA graphs of the chunk body, keyed by (clips, teacher forcing); valid while the workspace base is unchanged
+  struct GraphEntry { cudaGraphExec_t exec; char* ws_base; int warm; unsigned long long n_launches; };
+  std::map<int, GraphEntry> graphs;
+  bool use_graphs = true;
+  cudaStream_t gstream = nullptr; cudaEvent_t gev_in = nullptr, gev_out = nullptr;
+  void drop_graphs() {
+    for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+  }
 };
 
 void set_savgol_tables(const float* h5, const float* h9);

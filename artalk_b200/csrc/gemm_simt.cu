@@ -193,6 +193,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
   if (g.out_act) v = v && (((uintptr_t)g.out_act) % 16 == 0);
   p.vec_ok = v ? 1 : 0;
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.groups);
+  g_trace_dims[0] = g.M; g_trace_dims[1] = g.N; g_trace_dims[2] = g.K * g.groups;
   gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
   AT_LAUNCH_CHECK();
   return AT_OK;

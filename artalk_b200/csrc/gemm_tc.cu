@@ -399,6 +399,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p,
     attr_set = true;
   }
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  g_trace_dims[0] = p.rpb * p.n_batches; g_trace_dims[1] = p.N; g_trace_dims[2] = p.num_kb * BK * p.groups;
   gemm_tc_kernel<BN><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tmA, tmW, p);
   AT_LAUNCH_CHECK();
   return AT_OK;
@@ -429,7 +430,23 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.n_batches = batched ? ceil_div(g.M, g.a_map.rpb) : 1;
   AT_REQUIRE(!batched || g.M % g.a_map.rpb == 0, "gemm_tc: M must be a multiple of the A view's rows per batch");
   p.tiles_per_batch = ceil_div(p.rpb, BM);
-  const int BN = g.N >= 256 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : 32;
+  // N-tile choice: persistent CTAs on 148 SMs quantise badly for the recurrence's small GEMMs (e.g. 50 x 3 tiles of
+  // 128x256 = 2 waves at 51 %); score each candidate by wave efficiency x a per-tile MMA/smem efficiency factor
+  int BN = 32;
+  {
+    const int cand[4] = {256, 128, 64, 32};
+    const double eff[4] = {1.0, 0.92, 0.70, 0.45};
+    double best = -1.0;
+    const long m_tiles = (long)g.groups * p.n_batches * p.tiles_per_batch;
+    for (int i = 0; i < 4; ++i) {
+      if (cand[i] > 32 && cand[i] / 2 >= g.N) continue;          // tile mostly padding
+      const long tiles = m_tiles * ceil_div(g.N, cand[i]);
+      const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+      const double pad = (double)g.N / ((double)ceil_div(g.N, cand[i]) * cand[i]);
+      const double score = (double)tiles / (double)(waves * g_num_sms) * eff[i] * pad;
+      if (score > best) { best = score; BN = cand[i]; }
+    }
+  }
   p.n_tiles_n = ceil_div(g.N, BN);
   p.groups = g.groups;
   p.total_tiles = p.groups * p.n_batches * p.tiles_per_batch * p.n_tiles_n;

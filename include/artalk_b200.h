@@ -66,6 +66,9 @@ int artalk_finalize(artalk_engine_t* e);
 /* soft budget (bytes) used to size wav2vec sub-batches; the library grows its device workspace on demand */
 int artalk_set_workspace_limit(artalk_engine_t* e, size_t bytes);
 size_t artalk_workspace_bytes(const artalk_engine_t* e);
+/* the body of artalk_ar_chunk is replayed from a CUDA graph after one eager warm-up per (n_clips, teacher forcing);
+ * enable = 0 drops the graphs and launches eagerly (default: enabled) */
+int artalk_enable_graphs(artalk_engine_t* e, int enable);
 
 /* --- Wav2Vec2Model.forward + multi-scale area pooling (app/modules/wav2vec.py:11-27, app/models.py:93-95) ---
  * audio [n_chunks, chunk_samples] f32 (each row normalised on its own) -> cond [n_chunks, 181, 1024] f32 */
@@ -124,6 +127,11 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
  * stream; artalk_profile_read synchronises and fills host_out8 = {gemm launches, gemm ms, gemm flops, attention
  * launches, attention ms, attention flops, 0, 0} accumulated since the last enable call. */
 unsigned long long artalk_launch_count(void);
+/* launch trace: between begin and end every kernel launch of the library records a CUDA event on its stream;
+ * artalk_trace_end synchronises and writes "launcher,d0,d1,d2,microseconds" lines (time since the previous launch's
+ * completion) into host_buf; returns the byte count (a value >= cap means the buffer was too small), -1 on error */
+int artalk_trace_begin(void* stream);
+long artalk_trace_end(char* host_buf, long cap, void* stream);
 int artalk_profile_enable(artalk_engine_t* e, int enable);
 int artalk_profile_read(artalk_engine_t* e, double* host_out8, void* stream);
 
