@@ -141,7 +141,7 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU path)"
     import torch.distributed as dist
-    from artalk_b200 import _lib
+    from artalk_b200 import _lib, parallel
     from artalk_b200.engine import ARTAvatarInferEngine
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -157,21 +157,18 @@ def main():
     style_host = synthetic.make_style_motion(B, first_clip=rank * B).pin_memory()
     audio_dev, style_dev = audio_host.to(dev), style_host.to(dev)
     out_host = torch.empty(B, frames, 106).pin_memory()
-    gathered = torch.empty(world * B, frames, 106, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def step_resident():
         m = eng.inference_batch(audio_dev, style_dev)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, m)
-        return m
+        return parallel.gather_motion(m, world * B) if world > 1 else m      # the path's only collective
 
     def step_e2e():
         a = audio_host.to(dev, non_blocking=True)
         s = style_host.to(dev, non_blocking=True)
         m = eng.inference_batch(a, s)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, m)
+            parallel.gather_motion(m, world * B)
         out_host.copy_(m, non_blocking=True)
         return m
 
