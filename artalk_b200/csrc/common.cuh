@@ -73,6 +73,19 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   float inner = k0 * (x + k1 * x * x * x);
   return 0.5f * x * (1.0f + tanhf(inner));
 }
+// bf16-path erf-GELU: Abramowitz-Stegun 7.1.26, erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z),
+// |abs err| <= 1.5e-7 (plus ~1e-7 from the MUFU exp/rcp) — far below the bf16 rounding of the result
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = 1.0f - poly * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 // bf16-path variant: hardware tanh.approx (rel. error ~2^-11, below bf16 rounding of the result)
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

@@ -677,12 +677,20 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
                             prev_tok, adt, B, 0, c.n_levels - 1, C, st));
   g = gemm_args();
   g.A = prev_tok; g.a_map = plain_rows(C); g.W = getw("ar.prevkv.w"); g.ldw = C; g.M = (int)BL; g.N = NL * 2 * C; g.K = C;
-  g.bias = get<float>("ar.prevkv.b"); g.out_act = kvtmp; g.out_act_dt = adt; g.c_map = plain_rows(NL * 2 * C);
-  AT_TRY(gemm(g, st));
-  for (int l = 0; l < NL; ++l)
-    AT_TRY(launch_qkv_norm_scatter(kvtmp + (size_t)l * 2 * C * s, adt, (int64_t)NL * 2 * C, 0, nullptr, nullptr,
-                                   kcache + (size_t)l * B * KV * C * s, vcache + (size_t)l * B * KV * C * s,
-                                   batched_rows(P, (int64_t)KV * C, C), (int)BL, c.ar_heads, st));
+  g.bias = get<float>("ar.prevkv.b");
+  const bool fused_qkv = (adt == DT_BF16);      // tcgen05 epilogue normalises k heads and writes the caches directly
+  if (fused_qkv) {
+    g.qkv_mode = 2; g.qkv_C = C; g.kcache = kcache; g.vcache = vcache; g.kv_map = batched_rows(P, (int64_t)KV * C, C);
+    g.kv_layer_stride = (int64_t)B * KV * C;
+    AT_TRY(gemm(g, st));
+  } else {
+    g.out_act = kvtmp; g.out_act_dt = adt; g.c_map = plain_rows(NL * 2 * C);
+    AT_TRY(gemm(g, st));
+    for (int l = 0; l < NL; ++l)
+      AT_TRY(launch_qkv_norm_scatter(kvtmp + (size_t)l * 2 * C * s, adt, (int64_t)NL * 2 * C, 0, nullptr, nullptr,
+                                     kcache + (size_t)l * B * KV * C * s, vcache + (size_t)l * B * KV * C * s,
+                                     batched_rows(P, (int64_t)KV * C, C), (int)BL, c.ar_heads, st));
+  }
   for (int p = 0; p < c.n_levels; ++p) {
     const int n_new = c.patch_nums[p], off = p ? tb.cum[p - 1] : 0, M = B * n_new;
     const RowMap ada_map = batched_rows(n_new, (int64_t)L * n_ada, n_ada);
@@ -695,11 +703,19 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
       AT_TRY(launch_adaln_modulate(x, ada_l, adt, ada_map, 2 * C, 4 * C, u, adt, M, C, 1e-6f, st));
       g = gemm_args();
       g.A = u; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.qkv.w", l)); g.ldw = C; g.M = M; g.N = 3 * C; g.K = C;
-      g.bias = get<float>(S("ar.l%d.qkv.b", l)); g.out_act = kvtmp; g.out_act_dt = adt; g.c_map = plain_rows(3 * C);
-      AT_TRY(gemm(g, st));
+      g.bias = get<float>(S("ar.l%d.qkv.b", l));
       char* kc = kcache + (size_t)l * B * KV * C * s; char* vc = vcache + (size_t)l * B * KV * C * s;
-      AT_TRY(launch_qkv_norm_scatter(kvtmp, adt, 3 * C, 1, get<float>(S("ar.l%d.head_scale", l)), qbuf, kc + (size_t)(P + off) * C * s,
-                                     vc + (size_t)(P + off) * C * s, batched_rows(n_new, (int64_t)KV * C, C), M, c.ar_heads, st));
+      if (fused_qkv) {
+        g.qkv_mode = 1; g.qkv_C = C; g.head_scale = get<float>(S("ar.l%d.head_scale", l)); g.qbuf = qbuf;
+        g.kcache = kc + (size_t)(P + off) * C * s; g.vcache = vc + (size_t)(P + off) * C * s;
+        g.kv_map = batched_rows(n_new, (int64_t)KV * C, C);
+        AT_TRY(gemm(g, st));
+      } else {
+        g.out_act = kvtmp; g.out_act_dt = adt; g.c_map = plain_rows(3 * C);
+        AT_TRY(gemm(g, st));
+        AT_TRY(launch_qkv_norm_scatter(kvtmp, adt, 3 * C, 1, get<float>(S("ar.l%d.head_scale", l)), qbuf, kc + (size_t)(P + off) * C * s,
+                                       vc + (size_t)(P + off) * C * s, batched_rows(n_new, (int64_t)KV * C, C), M, c.ar_heads, st));
+      }
       AttnArgs a;
       a.q = qbuf; a.k = kc; a.v = vc; a.out = o; a.dt = adt; a.n_seq = B; a.n_heads = c.ar_heads; a.head_dim = 64;
       a.lq = n_new; a.lk = P + off + n_new;          // prev chunk + every current token of scale <= p

@@ -37,7 +37,25 @@ struct TcParams {
   float* out32; void* out_act; int out_act_dt; RowMap c_map;
   int vec_ok;
   unsigned int* err_flag;
+  int qkv_mode, qkv_C; const float* head_scale; bf16* qbuf; bf16* kcache; bf16* vcache; RowMap kv_map; int64_t kv_layer_stride;
 };
+
+// 64 fp32 values (one head of one row) -> bf16, 8 x 16-byte stores
+__device__ __forceinline__ void store_head_bf16(bf16* dst, const float (&a)[32], const float (&b)[32], float scale) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float* v = half ? b : a;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j] * scale, v[j + 1] * scale), h1 = __floats2bfloat162_rn(v[j + 2] * scale, v[j + 3] * scale);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4] * scale, v[j + 5] * scale), h3 = __floats2bfloat162_rn(v[j + 6] * scale, v[j + 7] * scale);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(dst + half * 32 + j) = pk;
+    }
+  }
+}
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -236,6 +254,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t g_off = (row_ok && p.gate) ? p.gate_map.off(r) + cg : 0;
       const int64_t r_off = (row_ok && p.resid) ? p.resid_map.off(r) + cg : 0;
       const float* bias = p.bias ? p.bias + g * p.bias_gs : nullptr;
+      if (p.qkv_mode) {
+        // fused AR q/k/v epilogue: this warp owns heads (64 columns = 2 TMEM chunks) of its column half
+        if constexpr (BN >= 128) {
+          const int period = (p.qkv_mode == 1 ? 3 : 2) * p.qkv_C;
+#pragma unroll 1
+          for (int hd = half * (BN / 128); hd < (half + 1) * (BN / 128); ++hd) {
+            float a[32], b2[32];
+            const uint32_t tcol = (uint32_t)(acc * BN + hd * 64);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol, a);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + 32, b2);
+            const int col0 = n_idx * BN + hd * 64;
+            if (!row_ok || col0 >= p.N) continue;
+            if (bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+                float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 32 + j));
+                a[j] += b0.x; a[j + 1] += b0.y; a[j + 2] += b0.z; a[j + 3] += b0.w;
+                b2[j] += b1.x; b2[j + 1] += b1.y; b2[j + 2] += b1.z; b2[j + 3] += b1.w;
+              }
+            }
+            const int layer = col0 / period, o = col0 - layer * period;
+            const int sec = o / p.qkv_C, hc = o - sec * p.qkv_C;
+            const bool is_q = (p.qkv_mode == 1 && sec == 0);
+            const bool is_k = (p.qkv_mode == 1) ? (sec == 1) : (sec == 0);
+            float scale = 1.0f;
+            if (is_q || is_k) {
+              float ss = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ss = fmaf(a[j], a[j], fmaf(b2[j], b2[j], ss));
+              scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);                     // F.normalize eps
+              if (is_q) scale *= p.head_scale[hc >> 6];
+            }
+            bf16* dst;
+            if (is_q) dst = p.qbuf + (int64_t)r * p.qkv_C + hc;
+            else dst = (is_k ? p.kcache : p.vcache) + (int64_t)layer * p.kv_layer_stride + p.kv_map.off(r) + hc;
+            store_head_bf16(dst, a, b2, scale);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        continue;
+      }
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         float v[32];
@@ -260,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         switch (p.act) {
           case ACT_GELU_ERF:
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
             break;
           case ACT_GELU_TANH:
 #pragma unroll
@@ -409,7 +471,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p,
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AT_OK;
-  AT_REQUIRE(g.A && g.W && (g.out32 || g.out_act), "gemm_tc: null operand");
+  AT_REQUIRE(g.A && g.W && (g.out32 || g.out_act || g.qkv_mode), "gemm_tc: null operand");
   AT_REQUIRE(g.K > 0 && g.K % 16 == 0, "gemm_tc: K=%d must be a positive multiple of 16", g.K);
   AT_REQUIRE(g.ldw % 8 == 0 && g.a_map.rs % 8 == 0 && g.a_map.bs % 8 == 0 && g.a_gs % 8 == 0 && g.w_gs % 8 == 0,
              "gemm_tc: operand strides must be multiples of 8 elements (16 bytes)");
@@ -439,6 +501,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     double best = -1.0;
     const long m_tiles = (long)g.groups * p.n_batches * p.tiles_per_batch;
     for (int i = 0; i < 4; ++i) {
+      if (g.qkv_mode && cand[i] < 128) continue;                 // fused q/k/v epilogue needs whole heads per warp
       if (cand[i] > 32 && cand[i] / 2 >= g.N) continue;          // tile mostly padding
       const long tiles = m_tiles * ceil_div(g.N, cand[i]);
       const long waves = (tiles + g_num_sms - 1) / g_num_sms;
@@ -456,6 +519,17 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
   p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;
   p.err_flag = g_err_flag;
+  p.qkv_mode = g.qkv_mode; p.qkv_C = g.qkv_C; p.head_scale = g.head_scale; p.qbuf = (bf16*)g.qbuf; p.kcache = (bf16*)g.kcache;
+  p.vcache = (bf16*)g.vcache; p.kv_map = g.kv_map; p.kv_layer_stride = g.kv_layer_stride;
+  if (g.qkv_mode) {
+    AT_REQUIRE((g.qkv_mode == 1 || g.qkv_mode == 2) && g.qkv_C > 0 && g.qkv_C % 64 == 0 && g.N % 64 == 0 &&
+               g.N % ((g.qkv_mode == 1 ? 3 : 2) * g.qkv_C) == 0, "gemm_tc: bad fused q/k/v shape (N=%d C=%d)", g.N, g.qkv_C);
+    AT_REQUIRE(g.kcache && g.vcache && (g.qkv_mode == 2 || (g.qbuf && g.head_scale)) && g.act == ACT_NONE && !g.gate && !g.resid,
+               "gemm_tc: bad fused q/k/v arguments");
+    AT_REQUIRE(g.kv_map.rs % 8 == 0 && g.kv_map.bs % 8 == 0 && g.kv_layer_stride % 8 == 0 && ((uintptr_t)g.kcache % 16 == 0) &&
+               ((uintptr_t)g.vcache % 16 == 0) && (!g.qbuf || (uintptr_t)g.qbuf % 16 == 0) &&
+               (!g.bias || ((uintptr_t)g.bias % 16 == 0)), "gemm_tc: fused q/k/v outputs must be 16-byte aligned");
+  }
   bool v = (g.c_map.rs % 8 == 0) && (g.c_map.bs % 8 == 0) && (g.c_gs % 8 == 0);
   if (g.bias) v = v && (((uintptr_t)g.bias) % 16 == 0) && (g.bias_gs % 4 == 0);
   if (g.gate) v = v && (g.gate_map.rs % 8 == 0) && (g.gate_map.bs % 8 == 0) && (((uintptr_t)g.gate) % 16 == 0);

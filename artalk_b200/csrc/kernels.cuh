@@ -43,6 +43,11 @@ struct GemmArgs {
   const void* gate; int gate_dt; RowMap gate_map;   // optional per-element multiplier gate[map(r)][c]
   const float* resid; RowMap resid_map;             // optional fp32 addend (may alias out32)
   float* out32; void* out_act; int out_act_dt; RowMap c_map;   // either/both outputs, same row map
+  // fused AR q/k/v epilogue (tcgen05 kernel only; app/transformer.py:68-74): output columns are blocks of qkv_C,
+  // mode 1 = [q | k | v], mode 2 = per layer [k | v] (period 2*qkv_C); q and k heads (64 wide) are L2-normalised
+  // (q additionally scaled by head_scale[head]); q -> qbuf[row][C], k/v -> caches at kv_map(row) (+ layer stride)
+  int qkv_mode; int qkv_C; const float* head_scale; void* qbuf; void* kcache; void* vcache; RowMap kv_map;
+  int64_t kv_layer_stride;
 };
 static inline GemmArgs gemm_args() {
   GemmArgs g;
@@ -51,6 +56,8 @@ static inline GemmArgs gemm_args() {
   g.bias = nullptr; g.act = ACT_NONE; g.gate = nullptr; g.gate_dt = DT_F32; g.gate_map = plain_rows(0);
   g.resid = nullptr; g.resid_map = plain_rows(0); g.out32 = nullptr; g.out_act = nullptr; g.out_act_dt = DT_F32;
   g.c_map = plain_rows(0);
+  g.qkv_mode = 0; g.qkv_C = 0; g.head_scale = nullptr; g.qbuf = nullptr; g.kcache = nullptr; g.vcache = nullptr;
+  g.kv_map = plain_rows(0); g.kv_layer_stride = 0;
   return g;
 }
 // fp32 CUDA-core GEMM (A and W fp32). gemm_simt.cu

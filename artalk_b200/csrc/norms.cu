@@ -37,7 +37,10 @@ __global__ void __launch_bounds__(128) ln_affine_kernel(const float* __restrict_
     if (gamma) load4(gamma + c, g);
     if (beta) load4(beta + c, b);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = apply_act((v[i][j] - mean) * rstd * g[j] + b[j], act);
+    for (int j = 0; j < 4; ++j) {
+      const float y = (v[i][j] - mean) * rstd * g[j] + b[j];
+      o[j] = (sizeof(TO) == 2 && act == ACT_GELU_ERF) ? gelu_erf_fast(y) : apply_act(y, act);   // bf16 output: fast erf
+    }
     store4(orow + c, o);
   }
 }
@@ -219,12 +222,104 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ au
   }
 }
 
+// Same computation with the lane's 16 channels x 10 taps of weights held in registers (kernel size <= 10): no
+// shared-memory weight traffic in the inner loop, x broadcast by shuffles. FAST = bf16 output path: erf-GELU through
+// the A&S 7.1.26 rational/exp form (|err| <= 1.5e-7) instead of erff.
+template <typename TO, bool FAST>
+__global__ void __launch_bounds__(256, 1) conv0_reg_kernel(const float* __restrict__ audio, const float2* __restrict__ stats,
+                                                           const float* __restrict__ w_kc, const float* __restrict__ bias,
+                                                           const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                           TO* __restrict__ out, int n_chunks, int n_samples, int l_out,
+                                                           int ksz, int stride, float eps) {
+  constexpr int KMAX = 10;
+  __shared__ __align__(16) float sb[3 * 512];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    sb[i] = bias[i]; sb[512 + i] = ln_g[i]; sb[1024 + i] = ln_b[i];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float w[KMAX][16];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      if (k < ksz) load4(w_kc + k * 512 + i * 128 + lane * 4, t);
+      w[k][i * 4 + 0] = t[0]; w[k][i * 4 + 1] = t[1]; w[k][i * 4 + 2] = t[2]; w[k][i * 4 + 3] = t[3];
+    }
+  __syncthreads();
+  const int64_t total = (int64_t)n_chunks * l_out;
+  const int64_t step = (int64_t)gridDim.x * 8;
+  // software prefetch of the next time step's samples (only 8 warps per SM: hide the global-load latency explicitly)
+  auto fetch = [&](int64_t i, float& raw, float2& st2) {
+    raw = 0.f; st2 = make_float2(0.f, 0.f);
+    if (i < total) {
+      const int ch = (int)(i / l_out), tt = (int)(i - (int64_t)ch * l_out);
+      st2 = stats[ch];
+      if (lane < ksz) raw = audio[(int64_t)ch * n_samples + (int64_t)tt * stride + lane];
+    }
+  };
+  float raw_n; float2 st_n;
+  fetch((int64_t)blockIdx.x * 8 + warp, raw_n, st_n);
+  for (int64_t idx = (int64_t)blockIdx.x * 8 + warp; idx < total; idx += step) {
+    const float2 stt = st_n;
+    const float xv = (lane < ksz) ? (raw_n - stt.x) * stt.y : 0.f;
+    fetch(idx + step, raw_n, st_n);
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float b4[4];
+      load4(sb + i * 128 + lane * 4, b4);
+      acc[i * 4] = b4[0]; acc[i * 4 + 1] = b4[1]; acc[i * 4 + 2] = b4[2]; acc[i * 4 + 3] = b4[3];
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const float xk = __shfl_sync(0xffffffffu, xv, k);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(w[k][j], xk, acc[j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += acc[j];
+    const float mean = warp_sum(s) * (1.0f / 512.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { float d = acc[j] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 512.0f) + eps);
+    TO* orow = out + idx * 512;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 128 + lane * 4;
+      float g[4], b[4], o[4];
+      load4(sb + 512 + c, g);
+      load4(sb + 1024 + c, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y = (acc[i * 4 + j] - mean) * rstd * g[j] + b[j];
+        o[j] = FAST ? gelu_erf_fast(y) : gelu_erf(y);
+      }
+      store4(orow + c, o);
+    }
+  }
+}
+
 int launch_conv0_ln_gelu(const float* audio, const float2* stats, const float* w_kc, const float* bias,
                          const float* ln_g, const float* ln_b, void* out, int out_dt, int n_chunks, int n_samples,
                          int l_out, int kernel, int stride, float eps, cudaStream_t st) {
   if (n_chunks <= 0) return AT_OK;
   AT_REQUIRE(kernel <= 32, "conv0: kernel size %d > 32", kernel);
   int64_t total = (int64_t)n_chunks * l_out;
+  if (kernel <= 10) {
+    int grid = (int)((total + 7) / 8);
+    if (grid > 148) grid = 148;                      // one 8-warp block per SM (weights live in registers)
+    if (out_dt == DT_F32)
+      conv0_reg_kernel<float, false><<<grid, 256, 0, st>>>(audio, stats, w_kc, bias, ln_g, ln_b, (float*)out, n_chunks, n_samples,
+                                                           l_out, kernel, stride, eps);
+    else
+      conv0_reg_kernel<bf16, true><<<grid, 256, 0, st>>>(audio, stats, w_kc, bias, ln_g, ln_b, (bf16*)out, n_chunks, n_samples,
+                                                         l_out, kernel, stride, eps);
+    AT_LAUNCH_CHECK();
+    return AT_OK;
+  }
   int grid = (int)((total + 7) / 8);
   if (grid > 148 * 8) grid = 148 * 8;
   size_t smem = (size_t)(kernel * 512 + 3 * 512) * sizeof(float);

@@ -52,7 +52,7 @@ def smooth_motion(motion: torch.Tensor, clip_length: Optional[int] = None, fix_p
 
 class ARTAvatarInferEngine:
     def __init__(self, load_gaga=False, fix_pose=False, clip_length=750, device="cuda", *, precision="bf16",
-                 state_dict=None, config=None, flame_asset=None, wav2vec=None, make_output_dir=True):
+                 state_dict=None, config=None, flame_asset=None, wav2vec=None, make_output_dir=True, lanes=1):
         if load_gaga:
             raise NotImplementedError("GAGAvatar rendering is outside the audio->motion path (use load_gaga=False)")
         self.device = device
@@ -64,7 +64,7 @@ class ARTAvatarInferEngine:
         configs = config if config is not None else json.load(open("./assets/config.json"))
         configs = json.loads(json.dumps(configs))
         configs["AR_CONFIG"]["AUDIO_ENCODER"] = audio_encoder
-        self.ARTalk = BitwiseARModel(configs, device=device, precision=precision, wav2vec=wav2vec).eval().to(device)
+        self.ARTalk = BitwiseARModel(configs, device=device, precision=precision, wav2vec=wav2vec, lanes=lanes).eval().to(device)
         self.ARTalk.load_state_dict(ckpt, strict=True)
         self.flame_model = FLAMEModel(n_shape=300, n_exp=100, scale=1.0, no_lmks=True, asset=flame_asset, device=device)
         self.mesh_renderer = None                      # pytorch3d RenderMesh: rendering is out of scope

@@ -110,6 +110,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=10.0, help="clip length")
     ap.add_argument("--config", default="FULL", choices=["FULL", "TINY"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=1, help="independent clip lanes (streams) per GPU")
     args = ap.parse_args()
     cfg = getattr(config, args.config)
     n_samples = int(args.seconds * cfg.sample_rate)
@@ -150,7 +151,7 @@ def main():
 
     eng = ARTAvatarInferEngine(load_gaga=False, clip_length=750, device=str(dev), precision=args.precision,
                                state_dict=synthetic.make_state_dict(cfg, 0), config=cfg.to_reference_json(),
-                               flame_asset=synthetic.make_flame_asset(0), wav2vec=cfg.wav2vec, make_output_dir=False)
+                               flame_asset=synthetic.make_flame_asset(0), wav2vec=cfg.wav2vec, make_output_dir=False, lanes=args.lanes)
     lib = _lib.lib()
     B = args.clips
     audio_host = synthetic.make_audio(B, n_samples, first_clip=rank * B).pin_memory()
@@ -208,6 +209,7 @@ def main():
     e2e_value = world * B * frames * args.steps / (e2e_ms / 1e3)
 
     # instrumented pass: CUDA events around every GEMM / attention launch of one step (not part of the timed numbers)
+    eng.ARTalk.lanes = 1                                 # serial launches on one engine handle for the attribution pass
     h = eng.ARTalk._handle()
     _lib.check(lib.artalk_profile_enable(h, 1))
     torch.cuda.synchronize(dev)
@@ -240,7 +242,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": workload, "l2": "256 MiB flush write between timed iterations", "weights": "seeded random init (no checkpoints ship)",
+            "config": {"workload": workload, "l2": "256 MiB flush write between timed iterations", "weights": "seeded random init (no checkpoints ship)", "lanes": args.lanes,
                        "parallelism": "clip-sharded replicas, 1 process/GPU, one NCCL all-gather of motion per step" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": audio_host.numel() * 4 + style_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},

@@ -195,6 +195,21 @@ def test_clip_subbatching_and_empty():
     assert short.shape == (1, 1, 106)
 
 
+def test_lanes_equal_single_lane():
+    """Two clip lanes on separate streams (shared weights, private workspaces/graphs) == one lane."""
+    _models.clear()
+    torch.cuda.empty_cache()
+    m = BitwiseARModel(config.TINY, device=DEV, precision="bf16", lanes=2)
+    m.load_state_dict(gu.state_dict("TINY"))
+    a, s = synthetic.make_audio(16, 70000), synthetic.make_style_motion(16)
+    two = m.inference({"audio": a, "style_motion": s})
+    two_again = m.inference({"audio": a, "style_motion": s})        # graph replay on both lanes
+    m.lanes = 1
+    one = m.inference({"audio": a, "style_motion": s})
+    assert torch.equal(two, one) and torch.equal(two, two_again)
+    m.close()
+
+
 def test_strict_state_dict():
     from artalk_b200.weights import CheckpointError
     sd = dict(gu.state_dict("TINY"))
