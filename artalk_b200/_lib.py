@@ -69,6 +69,7 @@ class FlameModelC(C.Structure):
         ("n_verts", C.c_int), ("n_shape", C.c_int), ("n_exp", C.c_int),
         ("v_template", C.c_void_p), ("dirs", C.c_void_p), ("j_template", C.c_void_p), ("j_dirs", C.c_void_p),
         ("lbs_weights", C.c_void_p), ("parents", C.c_int * 5), ("scale", C.c_float),
+        ("bsplit_full", C.c_void_p), ("ks_full", C.c_int), ("bsplit_expr", C.c_void_p), ("ks_expr", C.c_int),
     ]
 
 

@@ -102,6 +102,7 @@ static FlameModel to_flame(const artalk_flame_model_t* f) {
   m.j_template = f->j_template; m.j_dirs = f->j_dirs; m.lbs_weights = f->lbs_weights;
   for (int i = 0; i < 5; ++i) m.parents[i] = f->parents[i];
   m.scale = f->scale;
+  m.bsplit_full = f->bsplit_full; m.ks_full = f->ks_full; m.bsplit_expr = f->bsplit_expr; m.ks_expr = f->ks_expr;
   return m;
 }
 

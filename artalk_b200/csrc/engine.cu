@@ -237,13 +237,18 @@ int Engine::prof_begin(int enable) {
 // out8 = {gemm launches, gemm ms, gemm flops, attn launches, attn ms, attn flops, dropped, 0}
 int Engine::prof_read(double* out, cudaStream_t st) {
   AT_CUDA(cudaStreamSynchronize(st));
-  for (int i = 0; i < 8; ++i) out[i] = 0.0;
+  for (int i = 0; i < 12; ++i) out[i] = 0.0;
+  std::map<double, std::pair<double, double>> by_shape;        // GEMM flops per launch -> (launches, total ms)
   for (size_t i = 0; i < prof_cls.size(); ++i) {
     float ms = 0.f;
     AT_CUDA(cudaEventElapsedTime(&ms, prof_ev[2 * i], prof_ev[2 * i + 1]));
     int c = prof_cls[i] * 3;
     out[c] += 1.0; out[c + 1] += ms; out[c + 2] += prof_flops[i];
+    if (prof_cls[i] == 0) { auto& e = by_shape[prof_flops[i]]; e.first += 1.0; e.second += ms; }
   }
+  // out[6..8]: the dominant GEMM shape (largest summed duration): launches, total ms, flops per launch
+  for (auto& kv : by_shape)
+    if (kv.second.second > out[7]) { out[6] = kv.second.first; out[7] = kv.second.second; out[8] = kv.first; }
   return AT_OK;
 }
 

@@ -53,11 +53,27 @@ __global__ void __launch_bounds__(128) flame_coef_kernel(FlameDev fm, const floa
     float b = (l < fm.n_shape) ? shape[(int64_t)f * shape_rs + l] : expr[(int64_t)f * expr_rs + (l - fm.n_shape)];
     cf[l] = b;
 #pragma unroll
-    for (int i = 0; i < NJ * 3; ++i) jacc[i] = fmaf(b, fm.j_dirs[l * (NJ * 3) + i], jacc[i]);
+    for (int i = 0; i < NJ * 3; ++i) jacc[i] = fmaf(b, __ldg(fm.j_dirs + i * nb + l), jacc[i]);   // [15][nb]: coalesced over l
   }
 #pragma unroll
   for (int i = 0; i < NJ * 3; ++i) jacc[i] = warp_sum(jacc[i]) + fm.j_template[i];
-  if (lane != 0) return;
+  // hand the joints to flame_pose_kernel (one thread per frame) through the first 15 slots of the A region
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NJ * 3; ++i) cf[fm.n_bases + i] = jacc[i];
+  }
+}
+
+// one thread per frame: Rodrigues x5, pose feature (R[1:] - I), kinematic chain, relative transforms A
+__global__ void __launch_bounds__(128) flame_pose_kernel(FlameDev fm, const float* __restrict__ pose, int64_t pose_rs,
+                                                         int zero_global, float* __restrict__ coef, int n_frames) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const int nb = fm.n_shape + fm.n_exp, stride = fm.n_bases + COEF_A;
+  float* cf = coef + (int64_t)f * stride;
+  float jacc[NJ * 3];
+#pragma unroll
+  for (int i = 0; i < NJ * 3; ++i) jacc[i] = cf[fm.n_bases + i];
   const float* pp = pose + (int64_t)f * pose_rs;
   float rv[NJ][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
   if (!zero_global) { rv[0][0] = pp[0]; rv[0][1] = pp[1]; rv[0][2] = pp[2]; }
@@ -103,6 +119,23 @@ __global__ void __launch_bounds__(128) flame_coef_kernel(FlameDev fm, const floa
       a[0] = g[0]; a[1] = g[1]; a[2] = g[2];
       a[3] = g[3] - (g[0] * jacc[j * 3] + g[1] * jacc[j * 3 + 1] + g[2] * jacc[j * 3 + 2]);
     }
+}
+
+// static template for a shared shape row: out[e] = v_template[e] + sum_{l < n_l} beta[l] * dirs[l][e].
+// 64 elements x 4 basis groups per block (coalesced over e, 4-way split of the serial basis loop, smem reduce).
+__global__ void __launch_bounds__(256) flame_static_kernel(const float* __restrict__ v_template, const float* __restrict__ dirs,
+                                                           const float* __restrict__ beta, int n_l, int n_e, float* __restrict__ out) {
+  __shared__ float part[4][64];
+  const int el = threadIdx.x & 63, grp = threadIdx.x >> 6, e = blockIdx.x * 64 + el;
+  float acc = 0.f;
+  if (e < n_e) {
+    const int per = (n_l + 3) / 4, l0 = grp * per, l1 = min(n_l, l0 + per);
+#pragma unroll 5
+    for (int l = l0; l < l1; ++l) acc = fmaf(__ldg(beta + l), __ldg(dirs + (int64_t)l * n_e + e), acc);
+  }
+  part[grp][el] = acc;
+  __syncthreads();
+  if (grp == 0 && e < n_e) out[e] = v_template[e] + ((part[0][el] + part[1][el]) + (part[2][el] + part[3][el]));
 }
 
 // out[f][v][:] : SKIN ? scale * (sum_j w[v][j] A[f][j]) (base + blend, 1) : base + blend
@@ -176,7 +209,8 @@ __global__ void __launch_bounds__(128) flame_verts_kernel(FlameDev fm, const flo
 }  // namespace
 
 size_t flame_workspace_floats(const FlameModel& fm, int n_frames) {
-  return (size_t)n_frames * (fm.n_shape + fm.n_exp + 36 + COEF_A) + (size_t)fm.V * 3 + 64;
+  size_t ks = fm.ks_full > fm.ks_expr ? fm.ks_full : fm.ks_expr;                  // split-bf16 A operand: 3*KS bf16 per frame
+  return (size_t)n_frames * (fm.n_shape + fm.n_exp + 36 + COEF_A) + (size_t)fm.V * 3 + 128 + ((size_t)n_frames * 3 * ks + 1) / 2;
 }
 
 int launch_flame(const FlameModel& m, const float* shape, int64_t shape_rs, const float* expr, int64_t expr_rs,
@@ -194,17 +228,24 @@ int launch_flame(const FlameModel& m, const float* shape, int64_t shape_rs, cons
   flame_coef_kernel<<<ceil_div(n_frames, 4), 128, 0, st>>>(fm, shape, shape_rs, expr, expr_rs, pose, pose_rs, zero_global,
                                                            coef, n_frames);
   AT_LAUNCH_CHECK();
+  flame_pose_kernel<<<ceil_div(n_frames, 128), 128, 0, st>>>(fm, pose, pose_rs, zero_global, coef, n_frames);
+  AT_LAUNCH_CHECK();
   int l_begin = 0;
   const float* base = fm.v_template;
   dim3 grid_v(1, ceil_div(fm.V, 128));
   if (shape_rs == 0 && n_frames > 1 && fm.n_shape > 0) {
     // shared shape row: fold the shape bases into a static template once
-    size_t smem = (size_t)fm.n_shape * FB * sizeof(float);
-    AT_CUDA(cudaFuncSetAttribute(flame_verts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    flame_verts_kernel<false><<<grid_v, 128, smem, st>>>(fm, fm.v_template, 0, fm.n_shape, coef, stride, v_static, 1);
+    flame_static_kernel<<<ceil_div(fm.V * 3, 64), 256, 0, st>>>(fm.v_template, fm.dirs, coef, fm.n_shape, fm.V * 3, v_static);
     AT_LAUNCH_CHECK();
     base = v_static;
     l_begin = fm.n_shape;
+  }
+  // tensor-core path (flame_tc.cu) when the split-bf16 basis operands were provided
+  const void* bsplit = l_begin ? m.bsplit_expr : m.bsplit_full;
+  const int KS = l_begin ? m.ks_expr : m.ks_full;
+  if (bsplit && KS > 0) {
+    size_t a_off = ((size_t)n_frames * stride + (size_t)fm.V * 3 + 63) & ~(size_t)63;      // 256-byte aligned
+    return launch_flame_tc(m, base, coef, stride, l_begin, fm.n_bases - l_begin, bsplit, KS, ws + a_off, verts, n_frames, st);
   }
   size_t smem = ((size_t)(fm.n_bases - l_begin) * FB + FB * COEF_A) * sizeof(float);
   AT_CUDA(cudaFuncSetAttribute(flame_verts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));

@@ -123,7 +123,13 @@ struct FlameModel {
   const float* lbs_weights;               // [V][5]
   int parents[5];
   float scale;
+  // optional tensor-core operands (flame_tc.cu): dirs^T split into bf16 hi/lo, [V*3][3*KS] = [hi | hi | lo];
+  // *_full covers all n_shape+n_exp+36 bases, *_expr the last n_exp+36 (shared shape row). null -> fp32 CUDA-core kernel
+  const void* bsplit_full; int ks_full;
+  const void* bsplit_expr; int ks_expr;
 };
+int launch_flame_tc(const FlameModel& m, const float* base, const float* coef, int coef_stride, int l_begin, int n_l,
+                    const void* b_split, int KS, void* a_split_ws, float* verts, int n_frames, cudaStream_t st);
 // shape (N,300) [stride 0 allowed for a shared shape row], expr (N,100), pose6 (N,6) -> verts (N,V,3)
 int launch_flame(const FlameModel& fm, const float* shape, int64_t shape_rs, const float* expr, int64_t expr_rs,
                  const float* pose, int64_t pose_rs, int zero_global, float* coef_ws, float* verts, int n_frames,

@@ -16,7 +16,9 @@ class FLAMEModel:
     N_JOINTS = 5
 
     def __init__(self, n_shape, n_exp, scale=1.0, no_lmks=False, lmks_type="lmks70", *, asset=None, asset_path=None,
-                 device="cuda"):
+                 device="cuda", precision="tc"):
+        """precision: "tc" = blend on the tensor cores with split-bf16 operands (hi+lo, ~fp32 accuracy);
+        "fp32" = CUDA-core fp32 kernel."""
         if not no_lmks:
             raise NotImplementedError("landmark outputs (FLAME.py:150-204) are outside the audio->motion->mesh path; "
                                       "construct with no_lmks=True as inference.py:29 does")
@@ -47,14 +49,30 @@ class FLAMEModel:
             "v_template": v_template.reshape(-1).contiguous().to(self.device),
             "dirs": dirs.contiguous().to(self.device),
             "j_template": (jreg @ v_template).reshape(-1).contiguous().to(self.device),
-            "j_dirs": torch.einsum("jv,vkl->ljk", jreg, sdirs).reshape(nb, 15).contiguous().to(self.device),
+            "j_dirs": torch.einsum("jv,vkl->jkl", jreg, sdirs).reshape(15, nb).contiguous().to(self.device),   # [15][nb]
             "lbs_weights": fm["weights"].to(f32).contiguous().to(self.device),
         }
         self.parents = parents
+        if precision not in ("tc", "fp32"):
+            raise ValueError("precision must be 'tc' or 'fp32'")
+        self.precision = precision
+        if precision == "tc":
+            def split(d):                       # d: (n_l, V*3) fp32 -> [V*3][3*KS] bf16 = [hi | hi | lo]
+                n_l = d.shape[0]
+                ks = (n_l + 63) // 64 * 64
+                t = torch.zeros(V * 3, ks, dtype=torch.float32)
+                t[:, :n_l] = d.t()
+                hi = t.to(torch.bfloat16)
+                lo = (t - hi.float()).to(torch.bfloat16)
+                return torch.cat([hi, hi, lo], dim=1).contiguous().to(self.device), ks
+            self._bufs["bsplit_full"], ks_full = split(dirs)
+            self._bufs["bsplit_expr"], ks_expr = split(dirs[n_shape:])
         m = _lib.FlameModelC()
         m.n_verts, m.n_shape, m.n_exp = V, n_shape, nb - n_shape
         for k, t in self._bufs.items():
             setattr(m, k, t.data_ptr())
+        if precision == "tc":
+            m.ks_full, m.ks_expr = ks_full, ks_expr
         for i in range(5):
             m.parents[i] = int(parents[i])
         m.scale = self.scale

@@ -215,22 +215,36 @@ def main():
     torch.cuda.synchronize(dev)
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(); step_resident(); t1.record()
-    prof = (C.c_double * 8)()
+    prof = (C.c_double * 12)()
     _lib.check(lib.artalk_profile_read(h, prof, _lib.stream_ptr(dev)))
     _lib.check(lib.artalk_profile_enable(h, 0))
     torch.cuda.synchronize(dev)
     inst_ms = t0.elapsed_time(t1)
     hbm, tf_burst, tf_sus, src = peaks()
     n_g, ms_g, fl_g, n_a, ms_a, fl_a = [prof[i] for i in range(6)]
+    n_top, ms_top, fl_top = prof[6], prof[7], prof[8]          # dominant GEMM shape (largest summed duration)
     gemm_tflops = fl_g / (ms_g * 1e-3) / 1e12 if ms_g > 0 else 0.0
+    top_tflops = fl_top * n_top / (ms_top * 1e-3) / 1e12 if ms_top > 0 else 0.0
     peak = tf_sus if args.precision == "bf16" else 72.0
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all %d launches of one step)" % int(n_g)
-                if args.precision == "bf16" else "gemm_simt_kernel (fp32 CUDA-core GEMM)",
-                "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak, "traffic": None,
+    # ncu --set full capture of the dominant launch (profiles/r1c_ncu_full_summary.md): dram read + write per launch;
+    # only valid for the default workload's wav2vec FFN1 GEMM (M = clips*chunks*199 = 38208, N = 4096, K = 1024)
+    is_default_top = args.precision == "bf16" and abs(fl_top - 2.0 * 38208 * 4096 * 1024) < 1.0
+    roofline = {"bound": "tensor",
+                "kernel": ("gemm_tc_kernel<256> (tcgen05 bf16 GEMM), dominant shape of the step: %.1f GFLOP per launch, %d launches"
+                           % (fl_top / 1e9, int(n_top))) if args.precision == "bf16" else "gemm_simt_kernel (fp32 CUDA-core GEMM)",
+                "achieved": top_tflops, "peak": peak, "unit": "TFLOP/s", "frac": top_tflops / peak,
+                "traffic": 475.2e6 if is_default_top else None,
+                "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the two wav2vec FFN GEMMs that "
+                                "share this flop count: FFN1 38208x4096x1024 86.9+259.9 MB (algorithmic 78 A + 8 W + 313 out), "
+                                "FFN2 38208x1024x4096 480.7+122.8 MB (algorithmic 313 A + 8 W + 157 resid read + 157 write)"
+                if is_default_top else None,
                 "peak_source": ("%s bf16_tflops_sustained (kernel timed inside a long step)" % src) if args.precision == "bf16"
                 else "nominal fp32 FMA peak 148 SMs x 128 lanes x 2 x 1.9 GHz",
-                "flops_per_launch": fl_g / max(n_g, 1), "ms_per_launch": ms_g / max(n_g, 1),
-                "share_of_step": {"gemm": ms_g / inst_ms, "attention": ms_a / inst_ms, "other": max(0.0, 1 - (ms_g + ms_a) / inst_ms)},
+                "flops_per_launch": fl_top, "ms_per_launch": ms_top / max(n_top, 1),
+                "all_gemm_launches": {"launches": int(n_g), "achieved": gemm_tflops, "frac": gemm_tflops / peak,
+                                      "flops_per_launch": fl_g / max(n_g, 1), "ms_per_launch": ms_g / max(n_g, 1)},
+                "share_of_step": {"gemm": ms_g / inst_ms, "gemm_dominant_shape": ms_top / inst_ms, "attention": ms_a / inst_ms,
+                                  "other": max(0.0, 1 - (ms_g + ms_a) / inst_ms)},
                 "attention_tflops": fl_a / (ms_a * 1e-3) / 1e12 if ms_a > 0 else 0.0,
                 "path_tflops": B * n_chunks * GFLOP_PER_CHUNK * 1e9 / (total_ms / args.steps * 1e-3) / 1e12,
                 "path_frac_of_peak": B * n_chunks * GFLOP_PER_CHUNK * 1e9 / (total_ms / args.steps * 1e-3) / 1e12 / tf_sus}

@@ -106,6 +106,11 @@ typedef struct artalk_flame_model {
   const float* lbs_weights;  /* [V][5] */
   int parents[5];
   float scale;
+  /* optional tensor-core operands: dirs^T split into bf16 hi/lo, [V*3][3*ks] = [hi | hi | lo] (zero padded to ks, a
+   * multiple of 64). bsplit_full: all n_shape+n_exp+36 bases; bsplit_expr: the last n_exp+36 (used when all frames share
+   * one shape row). NULL selects the fp32 CUDA-core kernel. */
+  const void* bsplit_full; int ks_full;
+  const void* bsplit_expr; int ks_expr;
 } artalk_flame_model_t;
 size_t artalk_flame_workspace_floats(const artalk_flame_model_t* fm, int n_frames);
 /* shape [n, n_shape] (row stride shape_stride, 0 = one shared row), expr [n, n_exp], pose [n, 6] = (global rot, jaw);
@@ -124,7 +129,8 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
 /* --- measurement hooks (bench.py) ---
  * artalk_launch_count: kernels launched by this library in this process so far.
  * artalk_profile_enable(e, 1): bracket every GEMM / attention launch of the engine with CUDA events on the launching
- * stream; artalk_profile_read synchronises and fills host_out8 = {gemm launches, gemm ms, gemm flops, attention
+ * stream; artalk_profile_read synchronises and fills host_out8[12] (12 doubles; [6..8] = launches, total ms and flops per
+ * launch of the GEMM shape with the largest summed duration) = {gemm launches, gemm ms, gemm flops, attention
  * launches, attention ms, attention flops, 0, 0} accumulated since the last enable call. */
 unsigned long long artalk_launch_count(void);
 /* launch trace: between begin and end every kernel launch of the library records a CUDA event on its stream;

@@ -228,12 +228,14 @@ def test_strict_state_dict():
 
 
 # ----------------------------------------------------------------------------- FLAME + engine surface
-def test_flame_matches_golden_and_oracle():
+@pytest.mark.parametrize("fprec", ["tc", "fp32"])
+def test_flame_matches_golden_and_oracle(fprec):
+    """tc = tcgen05 blend with split-bf16 operands + skinning epilogue; fp32 = CUDA-core kernel."""
     g = gu.load("flame")
     asset = synthetic.make_flame_asset(0)
     shape, motion = flame_inputs()
     for scale in (1.0, 5.0):
-        fm = FLAMEModel(n_shape=300, n_exp=100, scale=scale, no_lmks=True, asset=asset, device=DEV)
+        fm = FLAMEModel(n_shape=300, n_exp=100, scale=scale, no_lmks=True, asset=asset, device=DEV, precision=fprec)
         vae = model("TINY", "fp32").basic_vae
         for wg in (False, True):
             v = vae.get_flame_verts(fm, shape.to(DEV), motion.to(DEV), with_global=wg).cpu()
@@ -241,7 +243,7 @@ def test_flame_matches_golden_and_oracle():
             assert v.shape == (6, 5023, 3)
             np.testing.assert_allclose(v.numpy(), g[key], atol=1e-4 * scale, rtol=0)
     # shared (expanded) shape row fast path == per-frame shape rows; 3-D shape loops over the batch
-    fm = FLAMEModel(n_shape=300, n_exp=100, scale=1.0, no_lmks=True, asset=asset, device=DEV)
+    fm = FLAMEModel(n_shape=300, n_exp=100, scale=1.0, no_lmks=True, asset=asset, device=DEV, precision=fprec)
     m37 = 0.3 * torch.randn(37, 106, generator=torch.Generator().manual_seed(1))
     sh1 = 0.5 * torch.randn(1, 300, generator=torch.Generator().manual_seed(2))
     v_shared = vae.get_flame_verts(fm, sh1.to(DEV).expand(37, -1), m37.to(DEV), with_global=True).cpu()
