@@ -96,6 +96,7 @@ SYMBOLS = {
     "artalk_set_savgol_tables": (C.c_int, [C.c_void_p, C.c_void_p]),
     "artalk_smooth_motion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "artalk_launch_count": (C.c_ulonglong, []),
+    "artalk_enable_pdl": (C.c_int, [C.c_int]),
     "artalk_trace_begin": (C.c_int, [C.c_void_p]),
     "artalk_trace_end": (C.c_long, [C.c_char_p, C.c_long, C.c_void_p]),
     "artalk_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
@@ -120,6 +121,8 @@ def lib() -> C.CDLL:
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(l, name)         # AttributeError if the ABI lost a symbol
             fn.restype, fn.argtypes = res, args
+        if os.environ.get("ARTALK_PDL", "1") == "0":      # developer switch: plain stream-order launches
+            l.artalk_enable_pdl(0)
         _lib = l
     return _lib
 

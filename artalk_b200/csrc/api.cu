@@ -134,6 +134,7 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
 }
 
 unsigned long long artalk_launch_count(void) { return g_launch_count; }
+int artalk_enable_pdl(int enable) { g_pdl = enable != 0; return AT_OK; }
 int artalk_trace_begin(void* stream) { return trace_begin((cudaStream_t)stream); }
 long artalk_trace_end(char* host_buf, long cap, void* stream) { return trace_end(host_buf, cap, (cudaStream_t)stream); }
 int artalk_profile_enable(artalk_engine_t* e, int enable) {

@@ -158,6 +158,28 @@ __device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = t;
 }
 
+// ---- programmatic dependent launch (PDL): kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (launch_k below), so a kernel's prologue overlaps the tail of its predecessor in the stream / CUDA graph. Every kernel
+// launched that way calls pdl_launch_dependents() early and pdl_wait() before it touches memory written by earlier
+// kernels (both are no-ops for a normally launched kernel); because every kernel waits before it finishes, completion
+// stays transitive along the stream.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+extern bool g_pdl;        // host switch (artalk_enable_pdl); default on
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t align_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 

@@ -178,6 +178,7 @@ void* Engine::ws_alloc(size_t bytes) {
   if (!var) return AT_ENOMEM
 
 unsigned long long g_launch_count = 0;
+bool g_pdl = true;
 
 // ------------------------------------------------------------------ launch trace
 bool g_trace_on = false;

@@ -27,6 +27,9 @@ struct TcParams {
   int N;
   int rpb;                 // rows per batch of the A view (tile rows never cross a batch)
   int n_batches, tiles_per_batch, n_tiles_n, groups, total_tiles;
+  // tail split: the last (partial) wave's tiles [main_tiles, main_tiles + r) are cut into `tail_split` column slices of
+  // `tail_bn` columns each, so the ragged wave costs tail_bn/BN of a full one (total_tiles counts the slices)
+  int main_tiles, tail_split, tail_bn;
   int num_kb;              // K blocks of 64
   int tap_mode, tap_pad;   // tap mode: k-block j reads rows shifted by (j - tap_pad), columns of group g
   int a_group_cols;        // column offset per group in the A view (tap mode)
@@ -148,9 +151,11 @@ template <int BN> struct TileCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// EPI: 0 = bias/activation only, 1 = gate and/or residual operands, 2 = fused AR q/k/v epilogue
+template <int BN, int EPI>
 __global__ void __launch_bounds__(384, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmWt, const TcParams p) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -170,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    if (p.tail_split > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWt)) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -185,29 +191,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  auto decode = [&](int tile, int& n_idx, int& mt, int& b, int& g) {
-    n_idx = tile % p.n_tiles_n;
-    int rest = tile / p.n_tiles_n;
+  // tile -> (M tile, batch, group, first column, width); tiles past main_tiles are column slices of the ragged wave
+  auto decode = [&](int tile, int& col_base, int& bn, int& mt, int& b, int& g) {
+    int big = tile, sub = 0;
+    bn = BN;
+    if (tile >= p.main_tiles) {
+      const int u = tile - p.main_tiles;
+      big = p.main_tiles + u / p.tail_split;
+      sub = u - (u / p.tail_split) * p.tail_split;
+      bn = p.tail_bn;
+    }
+    const int n_idx = big % p.n_tiles_n;
+    int rest = big / p.n_tiles_n;
     mt = rest % p.tiles_per_batch;
     rest /= p.tiles_per_batch;
     b = rest % p.n_batches;
     g = rest / p.n_batches;
+    col_base = n_idx * BN + sub * p.tail_bn;
   };
+  pdl_launch_dependents();       // the next kernel of the stream may start its own prologue
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      // weights do not depend on the previous kernel: the first ring fill of W is issued before the grid dependency
+      // resolves (programmatic dependent launch), the A tiles (activations) after it
+      int pre = 0;
+      if (blockIdx.x < p.total_tiles) {
+        int col_base, bn, mt, b, g;
+        decode(blockIdx.x, col_base, bn, mt, b, g);
+        pre = p.num_kb < STAGES ? p.num_kb : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_arrive_expect_tx(full_bar(kb), (uint32_t)(A_STAGE_BYTES + bn * BK * 2));
+          tma_load_3d(smem_base + kb * Cfg::STAGE_BYTES + A_STAGE_BYTES, bn == BN ? &tmW : &tmWt, full_bar(kb), kb * BK, col_base, g);
+        }
+      }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int n_idx, mt, b, g;
-        decode(tile, n_idx, mt, b, g);
+        int col_base, bn, mt, b, g;
+        decode(tile, col_base, bn, mt, b, g);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const bool w_done = pre > 0;
+          if (w_done) --pre;
+          else {
+            mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
+            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(A_STAGE_BYTES + bn * BK * 2));
+          }
           if (p.tap_mode) tma_load_3d(sa, &tmA, full_bar(stage), g * p.a_group_cols, mt * BM + kb - p.tap_pad, b);
           else tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, mt * BM, b);
-          tma_load_3d(sb, &tmW, full_bar(stage), kb * BK, n_idx * BN, g);
+          if (!w_done) tma_load_3d(sb, bn == BN ? &tmW : &tmWt, full_bar(stage), kb * BK, col_base, g);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -215,9 +249,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t idesc = make_idesc(tile >= p.main_tiles ? p.tail_bn : BN);
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u, p.err_flag, 2);
         tc_fence_after();
@@ -238,14 +272,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps, warp -> (TMEM lane quarter, column half) =====================
+    // One output row per thread. The row's gate / residual operands are requested before the accumulator is waited for:
+    // an L2 prefetch of every line the thread will touch when the tile starts (gate rows live in the 1.3 GB AdaLN table
+    // and always miss), and the chunk's loads are issued ahead of the tcgen05.ld so both latencies overlap.
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+    const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
     int it = 0;
+    pdl_wait();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      int n_idx, mt, b, g;
-      decode(tile, n_idx, mt, b, g);
+      int col_base, bn, mt, b, g;
+      decode(tile, col_base, bn, mt, b, g);
       const int acc = it & 1;
-      mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 4);
-      tc_fence_after();
       const int t_in_batch = mt * BM + q * 32 + lane;
       const bool row_ok = t_in_batch < p.rpb;
       const int r = b * p.rpb + t_in_batch;
@@ -254,17 +291,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t g_off = (row_ok && p.gate) ? p.gate_map.off(r) + cg : 0;
       const int64_t r_off = (row_ok && p.resid) ? p.resid_map.off(r) + cg : 0;
       const float* bias = p.bias ? p.bias + g * p.bias_gs : nullptr;
-      if (p.qkv_mode) {
-        // fused AR q/k/v epilogue: this warp owns heads (64 columns = 2 TMEM chunks) of its column half
-        if constexpr (BN >= 128) {
+      const int n_chunks = bn >> 5;
+      if (EPI == 1 && row_ok && p.vec_ok) {
+        for (int c = half; c < n_chunks; c += 2) {
+          const int col0 = col_base + c * 32;
+          if (col0 + 32 > p.N) break;
+          if (gate_bf) prefetch_l2(reinterpret_cast<const bf16*>(p.gate) + g_off + col0);
+          if (p.resid) prefetch_l2(p.resid + r_off + col0);
+        }
+      }
+      mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 4);
+      tc_fence_after();
+      if constexpr (EPI == 2) {
+        // fused AR q/k/v epilogue: a warp owns whole heads (64 columns = 2 TMEM chunks), heads alternate between the halves
+        {
           const int period = (p.qkv_mode == 1 ? 3 : 2) * p.qkv_C;
 #pragma unroll 1
-          for (int hd = half * (BN / 128); hd < (half + 1) * (BN / 128); ++hd) {
+          for (int hd = half; hd < (bn >> 6); hd += 2) {
             float a[32], b2[32];
             const uint32_t tcol = (uint32_t)(acc * BN + hd * 64);
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol, a);
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + 32, b2);
-            const int col0 = n_idx * BN + hd * 64;
+            const int col0 = col_base + hd * 64;
             if (!row_ok || col0 >= p.N) continue;
             if (bias) {
 #pragma unroll
@@ -293,18 +341,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             store_head_bf16(dst, a, b2, scale);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        continue;
-      }
+      } else {
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < n_chunks; c += 2) {
+        const int col0 = col_base + c * 32;
+        const bool live = row_ok && col0 < p.N;
+        const bool full = p.vec_ok && (col0 + 32 <= p.N);
+        // operand loads of this chunk go out before the accumulator read (independent of it)
+        uint4 gpre[4];
+        float4 rpre[8];
+        const bool pre_g = EPI == 1 && live && full && gate_bf, pre_r = EPI == 1 && live && full && p.resid != nullptr;
+        if (pre_g) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gpre[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gate) + g_off + col0) + j);
+        }
+        if (pre_r) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rpre[j] = *(reinterpret_cast<const float4*>(p.resid + r_off + col0) + j);
+        }
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-        const int col0 = n_idx * BN + c * 32;
-        if (!row_ok || col0 >= p.N) continue;
-        const bool full = p.vec_ok && (col0 + 32 <= p.N);
+        if (!live) continue;
         // ---- bias
         if (bias) {
           if (full) {
@@ -339,7 +396,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           default: break;
         }
         if (full) {
-          if (p.gate) {
+          if (pre_g) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {gpre[j].x, gpre[j].y, gpre[j].z, gpre[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                v[j * 8 + e * 2] *= __low2float(h); v[j * 8 + e * 2 + 1] *= __high2float(h);
+              }
+            }
+          } else if (EPI == 1 && p.gate) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float gv[4];
@@ -348,12 +415,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[j] *= gv[0]; v[j + 1] *= gv[1]; v[j + 2] *= gv[2]; v[j + 3] *= gv[3];
             }
           }
-          if (p.resid) {
+          if (pre_r) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float rv[4];
-              load4(p.resid + r_off + col0 + j, rv);
-              v[j] += rv[0]; v[j + 1] += rv[1]; v[j + 2] += rv[2]; v[j + 3] += rv[3];
+            for (int j = 0; j < 8; ++j) {
+              v[j * 4] += rpre[j].x; v[j * 4 + 1] += rpre[j].y; v[j * 4 + 2] += rpre[j].z; v[j * 4 + 3] += rpre[j].w;
             }
           }
           if (p.out32) {
@@ -385,10 +450,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) {
             if (col0 + j < p.N) {
               float t = v[j];
-              if (p.gate)
+              if (EPI == 1 && p.gate)
                 t *= (p.gate_dt == DT_F32) ? reinterpret_cast<const float*>(p.gate)[g_off + col0 + j]
                                            : __bfloat162float(reinterpret_cast<const bf16*>(p.gate)[g_off + col0 + j]);
-              if (p.resid) t += p.resid[r_off + col0 + j];
+              if (EPI == 1 && p.resid) t += p.resid[r_off + col0 + j];
               if (p.out32) p.out32[c_off + col0 + j] = t;
               if (p.out_act) {
                 if (p.out_act_dt == DT_F32) reinterpret_cast<float*>(p.out_act)[c_off + col0 + j] = t;
@@ -397,6 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -452,19 +518,28 @@ int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint
 unsigned int* g_err_flag = nullptr;
 int g_num_sms = 0;
 
-template <int BN>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t st) {
+template <int BN, int EPI>
+int launch_bn_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const TcParams& p, cudaStream_t st) {
   using Cfg = TileCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    AT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    AT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   g_trace_dims[0] = p.rpb * p.n_batches; g_trace_dims[1] = p.N; g_trace_dims[2] = p.num_kb * BK * p.groups;
-  gemm_tc_kernel<BN><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tmA, tmW, p);
+  AT_CUDA(launch_k(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, tmA, tmW, tmWt, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const TcParams& p, cudaStream_t st) {
+  if constexpr (BN >= 128) {
+    if (p.qkv_mode) return launch_bn_epi<BN, 2>(tmA, tmW, tmWt, p, st);
+  }
+  if (p.gate || p.resid) return launch_bn_epi<BN, 1>(tmA, tmW, tmWt, p, st);
+  return launch_bn_epi<BN, 0>(tmA, tmW, tmWt, p, st);
 }
 
 }  // namespace
@@ -492,27 +567,42 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.n_batches = batched ? ceil_div(g.M, g.a_map.rpb) : 1;
   AT_REQUIRE(!batched || g.M % g.a_map.rpb == 0, "gemm_tc: M must be a multiple of the A view's rows per batch");
   p.tiles_per_batch = ceil_div(p.rpb, BM);
-  // N-tile choice: persistent CTAs on 148 SMs quantise badly for the recurrence's small GEMMs (e.g. 50 x 3 tiles of
-  // 128x256 = 2 waves at 51 %); score each candidate by wave efficiency x a per-tile MMA/smem efficiency factor
-  int BN = 32;
+  // N-tile choice: persistent CTAs on 148 SMs quantise badly for the recurrence's GEMMs (e.g. 50 x 3 tiles of 128x256 =
+  // 1.01 waves). Cost model per candidate BN: full waves x time of a BN-wide tile + the ragged wave, whose tiles are cut
+  // into column slices (down to 32 columns, 64 for the fused q/k/v epilogue) when that lets them run side by side.
+  int BN = 32, tail_split = 1;
   {
     const int cand[4] = {256, 128, 64, 32};
-    const double eff[4] = {1.0, 0.92, 0.70, 0.45};
-    double best = -1.0;
+    const double tile_time[4] = {256.0, 139.0, 91.0, 71.0};      // BN / efficiency of a BN-wide tile (1, .92, .70, .45)
+    auto time_of = [&](int bn) { for (int i = 0; i < 4; ++i) if (cand[i] == bn) return tile_time[i]; return 71.0; };
+    const int min_slice = g.qkv_mode ? 64 : 32;
+    double best = 1e30;
     const long m_tiles = (long)g.groups * p.n_batches * p.tiles_per_batch;
     for (int i = 0; i < 4; ++i) {
       if (g.qkv_mode && cand[i] < 128) continue;                 // fused q/k/v epilogue needs whole heads per warp
       if (cand[i] > 32 && cand[i] / 2 >= g.N) continue;          // tile mostly padding
       const long tiles = m_tiles * ceil_div(g.N, cand[i]);
-      const long waves = (tiles + g_num_sms - 1) / g_num_sms;
-      const double pad = (double)g.N / ((double)ceil_div(g.N, cand[i]) * cand[i]);
-      const double score = (double)tiles / (double)(waves * g_num_sms) * eff[i] * pad;
-      if (score > best) { best = score; BN = cand[i]; }
+      const long waves = tiles / g_num_sms, rem = tiles % g_num_sms;
+      double cost = (double)waves * tile_time[i];
+      int split = 1;
+      if (rem > 0) {
+        if (waves > 0) while (cand[i] / (split * 2) >= min_slice && rem * split * 2 <= g_num_sms) split *= 2;
+        cost += time_of(cand[i] / split);
+      }
+      cost += 12.0;                                              // fixed per-launch latency (pipeline fill, epilogue drain)
+      if (cost < best) { best = cost; BN = cand[i]; tail_split = split; }
     }
   }
   p.n_tiles_n = ceil_div(g.N, BN);
   p.groups = g.groups;
-  p.total_tiles = p.groups * p.n_batches * p.tiles_per_batch * p.n_tiles_n;
+  {
+    const int tiles = p.groups * p.n_batches * p.tiles_per_batch * p.n_tiles_n;
+    const int rem = tail_split > 1 ? tiles % g_num_sms : 0;
+    p.main_tiles = tiles - rem;
+    p.tail_split = tail_split;
+    p.tail_bn = BN / tail_split;
+    p.total_tiles = p.main_tiles + rem * tail_split;
+  }
   p.num_kb = ceil_div(g.K, BK);
   p.tap_mode = g.tap_w > 0 ? 1 : 0; p.tap_pad = g.tap_pad; p.a_group_cols = (int)g.a_gs;
   p.c_gs = g.c_gs; p.bias_gs = g.bias_gs; p.bias = g.bias; p.act = g.act;
@@ -546,11 +636,14 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   AT_TRY(make_map_3d(&tmA, g.A, a_d0, (uint64_t)p.rpb, (uint64_t)p.n_batches, a_s1, a_s2 ? a_s2 : 16, BK, BM));
   const uint64_t w_s2 = g.groups > 1 ? (uint64_t)g.w_gs * 2 : (uint64_t)g.N * g.ldw * 2;
   AT_TRY(make_map_3d(&tmW, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.groups, (uint64_t)g.ldw * 2, w_s2, BK, (uint32_t)BN));
+  CUtensorMap tmWt = tmW;
+  if (p.tail_split > 1)
+    AT_TRY(make_map_3d(&tmWt, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.groups, (uint64_t)g.ldw * 2, w_s2, BK, (uint32_t)p.tail_bn));
   switch (BN) {
-    case 256: return launch_bn<256>(tmA, tmW, p, st);
-    case 128: return launch_bn<128>(tmA, tmW, p, st);
-    case 64: return launch_bn<64>(tmA, tmW, p, st);
-    default: return launch_bn<32>(tmA, tmW, p, st);
+    case 256: return launch_bn<256>(tmA, tmW, tmWt, p, st);
+    case 128: return launch_bn<128>(tmA, tmW, tmWt, p, st);
+    case 64: return launch_bn<64>(tmA, tmW, tmWt, p, st);
+    default: return launch_bn<32>(tmA, tmW, tmWt, p, st);
   }
 }
 

@@ -133,6 +133,10 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
  * launch of the GEMM shape with the largest summed duration) = {gemm launches, gemm ms, gemm flops, attention
  * launches, attention ms, attention flops, 0, 0} accumulated since the last enable call. */
 unsigned long long artalk_launch_count(void);
+/* programmatic dependent launch (default on): kernels are launched with the programmatic-stream-serialization attribute so
+ * a kernel's prologue (barrier init, TMEM allocation, weight prefetch) overlaps the tail of its predecessor; 0 = plain
+ * stream order. Process-wide; takes effect for launches (and CUDA-graph captures) made after the call. */
+int artalk_enable_pdl(int enable);
 /* launch trace: between begin and end every kernel launch of the library records a CUDA event on its stream;
  * artalk_trace_end synchronises and writes "launcher,d0,d1,d2,microseconds" lines (time since the previous launch's
  * completion) into host_buf; returns the byte count (a value >= cap means the buffer was too small), -1 on error */
