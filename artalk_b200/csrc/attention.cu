@@ -14,6 +14,7 @@ constexpr int WARPS = 4;
 
 template <typename T, int D>
 __global__ void __launch_bounds__(WARPS * 32) attn_kernel(AttnArgs a) {
+  pdl_enter();
   constexpr int DPL = D / 32;                 // output dims per lane
   __shared__ float Ks[KT][D + 1];
   __shared__ __align__(16) float Vs[KT][D];
@@ -128,11 +129,11 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   g_trace_dims[0] = a.n_seq * a.n_heads; g_trace_dims[1] = a.lq; g_trace_dims[2] = a.lk;
   dim3 grid(ceil_div(a.lq, WARPS * RPW), a.n_heads, a.n_seq);
   if (a.dt == DT_F32) {
-    if (a.head_dim == 64) attn_kernel<float, 64><<<grid, WARPS * 32, 0, st>>>(a);
-    else attn_kernel<float, 32><<<grid, WARPS * 32, 0, st>>>(a);
+    if (a.head_dim == 64) AT_CUDA(launch_k(attn_kernel<float, 64>, dim3(grid), dim3(WARPS * 32), 0, st, a));
+    else AT_CUDA(launch_k(attn_kernel<float, 32>, dim3(grid), dim3(WARPS * 32), 0, st, a));
   } else {
-    if (a.head_dim == 64) attn_kernel<bf16, 64><<<grid, WARPS * 32, 0, st>>>(a);
-    else attn_kernel<bf16, 32><<<grid, WARPS * 32, 0, st>>>(a);
+    if (a.head_dim == 64) AT_CUDA(launch_k(attn_kernel<bf16, 64>, dim3(grid), dim3(WARPS * 32), 0, st, a));
+    else AT_CUDA(launch_k(attn_kernel<bf16, 32>, dim3(grid), dim3(WARPS * 32), 0, st, a));
   }
   AT_LAUNCH_CHECK();
   return AT_OK;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256) qkv_norm_scatter_kernel(const T* __restri
                                                                const float* __restrict__ head_scale, T* __restrict__ qbuf,
                                                                T* __restrict__ kcache, T* __restrict__ vcache, RowMap kv_map,
                                                                int rows, int n_heads) {
+  pdl_enter();
   int C = n_heads * 64;
   int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -173,11 +175,11 @@ int launch_qkv_norm_scatter(const void* qkv, int dt, int64_t qkv_rs, int has_q, 
   int64_t warps = (int64_t)rows * n_heads;
   int grid = (int)((warps + 7) / 8);
   if (dt == DT_F32)
-    qkv_norm_scatter_kernel<float><<<grid, 256, 0, st>>>((const float*)qkv, qkv_rs, has_q, head_scale, (float*)qbuf,
-                                                         (float*)kcache, (float*)vcache, kv_map, rows, n_heads);
+    AT_CUDA(launch_k(qkv_norm_scatter_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)qkv, qkv_rs, has_q, head_scale, (float*)qbuf,
+                                                         (float*)kcache, (float*)vcache, kv_map, rows, n_heads));
   else
-    qkv_norm_scatter_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)qkv, qkv_rs, has_q, head_scale, (bf16*)qbuf,
-                                                        (bf16*)kcache, (bf16*)vcache, kv_map, rows, n_heads);
+    AT_CUDA(launch_k(qkv_norm_scatter_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)qkv, qkv_rs, has_q, head_scale, (bf16*)qbuf,
+                                                        (bf16*)kcache, (bf16*)vcache, kv_map, rows, n_heads));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

@@ -16,6 +16,7 @@ __device__ __forceinline__ float bit_val(uint32_t w, int c) { return ((w >> c) &
 // ---------------------------------------------------------------- argmax over bit pairs
 __global__ void __launch_bounds__(256) argmax_bits_kernel(const float* __restrict__ logits, RowMap l_map,
                                                           uint32_t* __restrict__ words, RowMap w_map, int rows) {
+  pdl_enter();
   int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   float2 l = *reinterpret_cast<const float2*>(logits + l_map.off(row) + lane * 2);
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(256) argmax_bits_kernel(const float* __restric
 
 int launch_argmax_bits(const float* logits, RowMap l_map, uint32_t* words, RowMap w_map, int rows, cudaStream_t st) {
   if (rows <= 0) return AT_OK;
-  argmax_bits_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(logits, l_map, words, w_map, rows);
+  AT_CUDA(launch_k(argmax_bits_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, logits, l_map, words, w_map, rows));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) bits_tokens_kernel(BitsTables tb, const u
                                                           const float* __restrict__ style, const float* __restrict__ embed_w,
                                                           const float* __restrict__ embed_b, const float* __restrict__ pos,
                                                           TO* __restrict__ out, int q_lo, int q_hi, int C) {
+  pdl_enter();
   __shared__ uint32_t sw[256];
   __shared__ float f_hat[MAXT][CD];
   __shared__ float feat[MAXT][CD];
@@ -100,9 +102,9 @@ int launch_bits_tokens(const BitsTables& tb, const uint32_t* words, int64_t word
   AT_REQUIRE(tb.T <= MAXT && tb.L <= 256 && q_lo >= 0 && q_hi < tb.n_levels && q_lo <= q_hi, "bits_tokens: bad levels");
   dim3 grid(n_clips, ceil_div(C, 256));
   if (out_dt == DT_F32)
-    bits_tokens_kernel<float><<<grid, 256, 0, st>>>(tb, words, words_cs, style, embed_w, embed_b, pos, (float*)out, q_lo, q_hi, C);
+    AT_CUDA(launch_k(bits_tokens_kernel<float>, dim3(grid), dim3(256), 0, st, tb, words, words_cs, style, embed_w, embed_b, pos, (float*)out, q_lo, q_hi, C));
   else
-    bits_tokens_kernel<bf16><<<grid, 256, 0, st>>>(tb, words, words_cs, style, embed_w, embed_b, pos, (bf16*)out, q_lo, q_hi, C);
+    AT_CUDA(launch_k(bits_tokens_kernel<bf16>, dim3(grid), dim3(256), 0, st, tb, words, words_cs, style, embed_w, embed_b, pos, (bf16*)out, q_lo, q_hi, C));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -111,6 +113,7 @@ int launch_bits_tokens(const BitsTables& tb, const uint32_t* words, int64_t word
 template <typename TO>
 __global__ void __launch_bounds__(256) bits_latent_kernel(BitsTables tb, const uint32_t* __restrict__ words, int64_t words_cs,
                                                           const float* __restrict__ dec_pos, TO* __restrict__ out, int half) {
+  pdl_enter();
   __shared__ uint32_t sw[256];
   const int clip = blockIdx.x, tid = threadIdx.x, T = tb.T;
   for (int i = tid; i < tb.L; i += blockDim.x) sw[i] = words[(int64_t)clip * words_cs + i];
@@ -134,8 +137,8 @@ int launch_bits_latent(const BitsTables& tb, const uint32_t* words, int64_t word
                        int out_dt, int n_clips, int half, cudaStream_t st) {
   if (n_clips <= 0) return AT_OK;
   AT_REQUIRE(tb.L <= 256 && tb.n_levels >= 2, "bits_latent: bad tables");
-  if (out_dt == DT_F32) bits_latent_kernel<float><<<n_clips, 256, 0, st>>>(tb, words, words_cs, dec_pos, (float*)out, half);
-  else bits_latent_kernel<bf16><<<n_clips, 256, 0, st>>>(tb, words, words_cs, dec_pos, (bf16*)out, half);
+  if (out_dt == DT_F32) AT_CUDA(launch_k(bits_latent_kernel<float>, dim3(n_clips), dim3(256), 0, st, tb, words, words_cs, dec_pos, (float*)out, half));
+  else AT_CUDA(launch_k(bits_latent_kernel<bf16>, dim3(n_clips), dim3(256), 0, st, tb, words, words_cs, dec_pos, (bf16*)out, half));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -143,6 +146,7 @@ int launch_bits_latent(const BitsTables& tb, const uint32_t* words, int64_t word
 // ---------------------------------------------------------------- residual multi-scale BSQ
 __global__ void __launch_bounds__(256) bsq_kernel(BitsTables tb, const float* __restrict__ enc_out, uint32_t* __restrict__ words,
                                                   int64_t words_cs) {
+  pdl_enter();
   __shared__ float r[MAXT][CD];
   __shared__ float qs[MAXT][CD];
   const int clip = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = tb.T;
@@ -190,7 +194,7 @@ int launch_bsq_quantize(const BitsTables& tb, const float* enc_out, uint32_t* wo
                         cudaStream_t st) {
   if (n_clips <= 0) return AT_OK;
   AT_REQUIRE(tb.T <= MAXT, "bsq: T too large");
-  bsq_kernel<<<n_clips, 256, 0, st>>>(tb, enc_out, words, words_cs);
+  AT_CUDA(launch_k(bsq_kernel, dim3(n_clips), dim3(256), 0, st, tb, enc_out, words, words_cs));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -200,6 +204,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256) motion_norm_pos_kernel(const float* __restrict__ motion, const float* __restrict__ mean,
                                                               const float* __restrict__ stdv, const float* __restrict__ pos,
                                                               TO* __restrict__ out, int64_t total, int T, int dim, int k_pad) {
+  pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % k_pad);
     int64_t row = i / k_pad;
@@ -216,8 +221,8 @@ int launch_motion_norm_pos(const float* motion, const float* mean, const float* 
   int64_t total = (int64_t)n_clips * T * k_pad;
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  if (out_dt == DT_F32) motion_norm_pos_kernel<float><<<grid, 256, 0, st>>>(motion, mean, stdv, pos, (float*)out, total, T, dim, k_pad);
-  else motion_norm_pos_kernel<bf16><<<grid, 256, 0, st>>>(motion, mean, stdv, pos, (bf16*)out, total, T, dim, k_pad);
+  if (out_dt == DT_F32) AT_CUDA(launch_k(motion_norm_pos_kernel<float>, dim3(grid), dim3(256), 0, st, motion, mean, stdv, pos, (float*)out, total, T, dim, k_pad));
+  else AT_CUDA(launch_k(motion_norm_pos_kernel<bf16>, dim3(grid), dim3(256), 0, st, motion, mean, stdv, pos, (bf16*)out, total, T, dim, k_pad));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

@@ -24,6 +24,7 @@ __device__ __forceinline__ float gate_at(const void* gate, int dt, int64_t off) 
 }
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
+  pdl_enter();
   __shared__ __align__(16) float As[2][BK][BM + PADM];
   __shared__ __align__(16) float Bs[2][BK][BN + PADM];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -194,7 +195,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
   p.vec_ok = v ? 1 : 0;
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.groups);
   g_trace_dims[0] = g.M; g_trace_dims[1] = g.N; g_trace_dims[2] = g.K * g.groups;
-  gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
+  AT_CUDA(launch_k(gemm_simt_kernel, dim3(grid), dim3(256), 0, st, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

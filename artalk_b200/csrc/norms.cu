@@ -11,6 +11,7 @@ template <int V4, typename TO>
 __global__ void __launch_bounds__(128) ln_affine_kernel(const float* __restrict__ x, int64_t x_rs, TO* __restrict__ out,
                                                         int64_t out_rs, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int rows, float eps, int act) {
+  pdl_enter();
   int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* xr = x + (int64_t)row * x_rs;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(128) ln_affine_kernel(const float* __restrict_
 template <int V4, typename TO>
 static int ln_launch(const float* x, int64_t x_rs, void* out, int64_t out_rs, const float* g, const float* b, int rows,
                      float eps, int act, cudaStream_t st) {
-  ln_affine_kernel<V4, TO><<<ceil_div(rows, 4), 128, 0, st>>>(x, x_rs, (TO*)out, out_rs, g, b, rows, eps, act);
+  AT_CUDA(launch_k(ln_affine_kernel<V4, TO>, dim3(ceil_div(rows, 4)), dim3(128), 0, st, x, x_rs, (TO*)out, out_rs, g, b, rows, eps, act));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -75,6 +76,7 @@ template <int V4, typename TA, typename TO>
 __global__ void __launch_bounds__(128) adaln_kernel(const float* __restrict__ x, const TA* __restrict__ ada, RowMap ada_map,
                                                     int scale_off, int shift_off, TO* __restrict__ out, int rows,
                                                     float eps) {
+  pdl_enter();
   constexpr int C = V4 * 128;
   int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -113,13 +115,13 @@ int launch_adaln_modulate(const float* x, const void* ada, int ada_dt, RowMap ad
   AT_REQUIRE(cols == 768, "adaln: width must be 768 (got %d)", cols);
   dim3 grid(ceil_div(rows, 4));
   if (ada_dt == DT_F32 && out_dt == DT_F32)
-    adaln_kernel<6, float, float><<<grid, 128, 0, st>>>(x, (const float*)ada, ada_map, scale_off, shift_off, (float*)out, rows, eps);
+    AT_CUDA(launch_k(adaln_kernel<6, float, float>, dim3(grid), dim3(128), 0, st, x, (const float*)ada, ada_map, scale_off, shift_off, (float*)out, rows, eps));
   else if (ada_dt == DT_BF16 && out_dt == DT_BF16)
-    adaln_kernel<6, bf16, bf16><<<grid, 128, 0, st>>>(x, (const bf16*)ada, ada_map, scale_off, shift_off, (bf16*)out, rows, eps);
+    AT_CUDA(launch_k(adaln_kernel<6, bf16, bf16>, dim3(grid), dim3(128), 0, st, x, (const bf16*)ada, ada_map, scale_off, shift_off, (bf16*)out, rows, eps));
   else if (ada_dt == DT_F32 && out_dt == DT_BF16)
-    adaln_kernel<6, float, bf16><<<grid, 128, 0, st>>>(x, (const float*)ada, ada_map, scale_off, shift_off, (bf16*)out, rows, eps);
+    AT_CUDA(launch_k(adaln_kernel<6, float, bf16>, dim3(grid), dim3(128), 0, st, x, (const float*)ada, ada_map, scale_off, shift_off, (bf16*)out, rows, eps));
   else
-    adaln_kernel<6, bf16, float><<<grid, 128, 0, st>>>(x, (const bf16*)ada, ada_map, scale_off, shift_off, (float*)out, rows, eps);
+    AT_CUDA(launch_k(adaln_kernel<6, bf16, float>, dim3(grid), dim3(128), 0, st, x, (const bf16*)ada, ada_map, scale_off, shift_off, (float*)out, rows, eps));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -127,6 +129,7 @@ int launch_adaln_modulate(const float* x, const void* ada, int ada_dt, RowMap ad
 // ---------------------------------------------------------------- audio statistics
 __global__ void __launch_bounds__(1024) audio_stats_kernel(const float* __restrict__ audio, int n_samples,
                                                            float2* __restrict__ stats) {
+  pdl_enter();
   __shared__ float red[32];
   const float* a = audio + (int64_t)blockIdx.x * n_samples;
   float s = 0.f;
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(1024) audio_stats_kernel(const float* __restri
 int launch_audio_stats(const float* audio, int n_chunks, int n_samples, float2* stats, cudaStream_t st) {
   if (n_chunks <= 0) return AT_OK;
   AT_REQUIRE(n_samples % 4 == 0 && n_samples > 1, "audio_stats: n_samples must be a multiple of 4");
-  audio_stats_kernel<<<n_chunks, 1024, 0, st>>>(audio, n_samples, stats);
+  AT_CUDA(launch_k(audio_stats_kernel, dim3(n_chunks), dim3(1024), 0, st, audio, n_samples, stats));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ au
                                                     const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                                                     TO* __restrict__ out, int n_chunks, int n_samples, int l_out,
                                                     int ksz, int stride, float eps) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* sw = sm;                    // [ksz][512]
   float* sb = sw + ksz * 512;        // bias, gamma, beta: 3 x 512
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(256, 1) conv0_reg_kernel(const float* __restri
                                                            const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                                                            TO* __restrict__ out, int n_chunks, int n_samples, int l_out,
                                                            int ksz, int stride, float eps) {
+  pdl_enter();
   constexpr int KMAX = 10;
   __shared__ __align__(16) float sb[3 * 512];
   for (int i = threadIdx.x; i < 512; i += blockDim.x) {
@@ -312,11 +317,11 @@ int launch_conv0_ln_gelu(const float* audio, const float2* stats, const float* w
     int grid = (int)((total + 7) / 8);
     if (grid > 148) grid = 148;                      // one 8-warp block per SM (weights live in registers)
     if (out_dt == DT_F32)
-      conv0_reg_kernel<float, false><<<grid, 256, 0, st>>>(audio, stats, w_kc, bias, ln_g, ln_b, (float*)out, n_chunks, n_samples,
-                                                           l_out, kernel, stride, eps);
+      AT_CUDA(launch_k(conv0_reg_kernel<float, false>, dim3(grid), dim3(256), 0, st, audio, stats, w_kc, bias, ln_g, ln_b, (float*)out, n_chunks, n_samples,
+                                                           l_out, kernel, stride, eps));
     else
-      conv0_reg_kernel<bf16, true><<<grid, 256, 0, st>>>(audio, stats, w_kc, bias, ln_g, ln_b, (bf16*)out, n_chunks, n_samples,
-                                                         l_out, kernel, stride, eps);
+      AT_CUDA(launch_k(conv0_reg_kernel<bf16, true>, dim3(grid), dim3(256), 0, st, audio, stats, w_kc, bias, ln_g, ln_b, (bf16*)out, n_chunks, n_samples,
+                                                         l_out, kernel, stride, eps));
     AT_LAUNCH_CHECK();
     return AT_OK;
   }
@@ -324,11 +329,11 @@ int launch_conv0_ln_gelu(const float* audio, const float2* stats, const float* w
   if (grid > 148 * 8) grid = 148 * 8;
   size_t smem = (size_t)(kernel * 512 + 3 * 512) * sizeof(float);
   if (out_dt == DT_F32)
-    conv0_kernel<float><<<grid, 256, smem, st>>>(audio, stats, w_kc, bias, ln_g, ln_b, (float*)out, n_chunks, n_samples,
-                                                 l_out, kernel, stride, eps);
+    AT_CUDA(launch_k(conv0_kernel<float>, dim3(grid), dim3(256), smem, st, audio, stats, w_kc, bias, ln_g, ln_b, (float*)out, n_chunks, n_samples,
+                                                 l_out, kernel, stride, eps));
   else
-    conv0_kernel<bf16><<<grid, 256, smem, st>>>(audio, stats, w_kc, bias, ln_g, ln_b, (bf16*)out, n_chunks, n_samples,
-                                                l_out, kernel, stride, eps);
+    AT_CUDA(launch_k(conv0_kernel<bf16>, dim3(grid), dim3(256), smem, st, audio, stats, w_kc, bias, ln_g, ln_b, (bf16*)out, n_chunks, n_samples,
+                                                l_out, kernel, stride, eps));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -338,6 +343,7 @@ struct PoolLevels { int n; int pn[8]; int cum[8]; };
 
 __global__ void __launch_bounds__(256) audio_pool_kernel(const float* __restrict__ x, float* __restrict__ cond, int l_in,
                                                          int cols, PoolLevels lv, int l_out) {
+  pdl_enter();
   int chunk = blockIdx.y, orow = blockIdx.x;
   int level = 0;
   while (level + 1 < lv.n && orow >= lv.cum[level]) ++level;
@@ -369,7 +375,7 @@ int launch_audio_pool(const float* x, float* cond, int n, int l_in, int cols, co
   int c = 0;
   for (int i = 0; i < n_levels; ++i) { lv.pn[i] = patch_nums[i]; c += patch_nums[i]; lv.cum[i] = c; }
   dim3 grid(c, n);
-  audio_pool_kernel<<<grid, 256, 0, st>>>(x, cond, l_in, cols, lv, c);
+  AT_CUDA(launch_k(audio_pool_kernel, dim3(grid), dim3(256), 0, st, x, cond, l_in, cols, lv, c));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -378,6 +384,7 @@ int launch_audio_pool(const float* x, float* cond, int n, int l_in, int cols, co
 template <typename TO>
 __global__ void __launch_bounds__(256) act_cast_kernel(const float* __restrict__ x, RowMap x_map, TO* __restrict__ out,
                                                        int rows, int cols, int act) {
+  pdl_enter();
   int c4 = cols >> 2;
   int64_t total = (int64_t)rows * c4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -396,8 +403,8 @@ int launch_act_cast(const float* x, RowMap x_map, void* out, int out_dt, int row
   int64_t total = (int64_t)rows * (cols / 4);
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  if (out_dt == DT_F32) act_cast_kernel<float><<<grid, 256, 0, st>>>(x, x_map, (float*)out, rows, cols, act);
-  else act_cast_kernel<bf16><<<grid, 256, 0, st>>>(x, x_map, (bf16*)out, rows, cols, act);
+  if (out_dt == DT_F32) AT_CUDA(launch_k(act_cast_kernel<float>, dim3(grid), dim3(256), 0, st, x, x_map, (float*)out, rows, cols, act));
+  else AT_CUDA(launch_k(act_cast_kernel<bf16>, dim3(grid), dim3(256), 0, st, x, x_map, (bf16*)out, rows, cols, act));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

@@ -31,6 +31,7 @@ __device__ __forceinline__ float savgol_at(const float* __restrict__ x, int64_t 
 
 __global__ void __launch_bounds__(256) savgol_post_kernel(const float* __restrict__ motion, float* __restrict__ out, int T,
                                                           int T_out, int dim, int fix_pose, int zero_tail, SavgolTables tb, int64_t total) {
+  pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % dim);
     int64_t rt = i / dim;
@@ -53,7 +54,7 @@ int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int 
   int64_t total = (int64_t)n_clips * T_out * dim;
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  savgol_post_kernel<<<grid, 256, 0, st>>>(motion, out, T, T_out, dim, fix_pose, zero_tail, g_tables, total);
+  AT_CUDA(launch_k(savgol_post_kernel, dim3(grid), dim3(256), 0, st, motion, out, T, T_out, dim, fix_pose, zero_tail, g_tables, total));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
