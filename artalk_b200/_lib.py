@@ -97,6 +97,7 @@ SYMBOLS = {
     "artalk_smooth_motion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "artalk_launch_count": (C.c_ulonglong, []),
     "artalk_enable_pdl": (C.c_int, [C.c_int]),
+    "artalk_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "artalk_trace_begin": (C.c_int, [C.c_void_p]),
     "artalk_trace_end": (C.c_long, [C.c_char_p, C.c_long, C.c_void_p]),
     "artalk_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
@@ -123,6 +124,8 @@ def lib() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         if os.environ.get("ARTALK_PDL", "1") == "0":      # developer switch: plain stream-order launches
             l.artalk_enable_pdl(0)
+        if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":
+            l.artalk_set_option(b"gemm_pair", 0)
         _lib = l
     return _lib
 

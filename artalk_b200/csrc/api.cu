@@ -135,6 +135,13 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
 
 unsigned long long artalk_launch_count(void) { return g_launch_count; }
 int artalk_enable_pdl(int enable) { g_pdl = enable != 0; return AT_OK; }
+int artalk_set_option(const char* name, int value) {
+  AT_REQUIRE(name, "artalk_set_option: null name");
+  if (!std::strcmp(name, "pdl")) { g_pdl = value != 0; return AT_OK; }
+  if (!std::strcmp(name, "gemm_pair")) { set_gemm_pair_mode(value); return AT_OK; }
+  set_last_error("artalk_set_option: unknown option '%s'", name);
+  return AT_EINVAL;
+}
 int artalk_trace_begin(void* stream) { return trace_begin((cudaStream_t)stream); }
 long artalk_trace_end(char* host_buf, long cap, void* stream) { return trace_end(host_buf, cap, (cudaStream_t)stream); }
 int artalk_profile_enable(artalk_engine_t* e, int enable) {

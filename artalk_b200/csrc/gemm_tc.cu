@@ -12,6 +12,7 @@
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue (lane quarter x column half).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include "kernels.cuh"
@@ -150,6 +151,130 @@ template <int BN> struct TileCfg {
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// One 32-column chunk of one output row: out = resid + gate * act(acc + bias). The chunk's gate / residual loads are issued
+// ahead of the tcgen05.ld of the accumulator so both latencies overlap. Shared by the 1-CTA and the CTA-pair kernels.
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, bool row_ok, int64_t c_off, int64_t g_off, int64_t r_off,
+                                          const float* bias, int col0, bool gate_bf) {
+    const bool live = row_ok && col0 < p.N;
+    const bool full = p.vec_ok && (col0 + 32 <= p.N);
+    // operand loads of this chunk go out before the accumulator read (independent of it)
+    uint4 gpre[4];
+    float4 rpre[8];
+    const bool pre_g = EPI == 1 && live && full && gate_bf, pre_r = EPI == 1 && live && full && p.resid != nullptr;
+    if (pre_g) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gpre[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gate) + g_off + col0) + j);
+    }
+    if (pre_r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rpre[j] = *(reinterpret_cast<const float4*>(p.resid + r_off + col0) + j);
+    }
+    float v[32];
+    tmem_ld32(taddr, v);
+    if (!live) return;
+    // ---- bias
+    if (bias) {
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+          v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
+      }
+    }
+    // ---- activation (switch hoisted out of the element loop; fast-math variants: outputs are rounded to bf16)
+    switch (p.act) {
+      case ACT_GELU_ERF:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        break;
+      case ACT_GELU_TANH:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+        break;
+      case ACT_LEAKY02:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+        break;
+      case ACT_SILU:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+        break;
+      default: break;
+    }
+    if (full) {
+      if (pre_g) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w[4] = {gpre[j].x, gpre[j].y, gpre[j].z, gpre[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+            v[j * 8 + e * 2] *= __low2float(h); v[j * 8 + e * 2 + 1] *= __high2float(h);
+          }
+        }
+      } else if (EPI == 1 && p.gate) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float gv[4];
+          if (p.gate_dt == DT_F32) load4(reinterpret_cast<const float*>(p.gate) + g_off + col0 + j, gv);
+          else load4(reinterpret_cast<const bf16*>(p.gate) + g_off + col0 + j, gv);
+          v[j] *= gv[0]; v[j + 1] *= gv[1]; v[j + 2] *= gv[2]; v[j + 3] *= gv[3];
+        }
+      }
+      if (pre_r) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j * 4] += rpre[j].x; v[j * 4 + 1] += rpre[j].y; v[j * 4 + 2] += rpre[j].z; v[j * 4 + 3] += rpre[j].w;
+        }
+      }
+      if (p.out32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(p.out32 + c_off + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      if (p.out_act) {
+        if (p.out_act_dt == DT_F32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + c_off + col0 + j) =
+                make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_act) + c_off + col0 + j) = pk;
+          }
+        }
+      }
+    } else {
+      // ragged / unaligned tail: fully unrolled with compile-time indices so v[] stays in registers
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < p.N) {
+          float t = v[j];
+          if (EPI == 1 && p.gate)
+            t *= (p.gate_dt == DT_F32) ? reinterpret_cast<const float*>(p.gate)[g_off + col0 + j]
+                                       : __bfloat162float(reinterpret_cast<const bf16*>(p.gate)[g_off + col0 + j]);
+          if (EPI == 1 && p.resid) t += p.resid[r_off + col0 + j];
+          if (p.out32) p.out32[c_off + col0 + j] = t;
+          if (p.out_act) {
+            if (p.out_act_dt == DT_F32) reinterpret_cast<float*>(p.out_act)[c_off + col0 + j] = t;
+            else reinterpret_cast<bf16*>(p.out_act)[c_off + col0 + j] = __float2bfloat16_rn(t);
+          }
+        }
+      }
+    }
+}
 
 // EPI: 0 = bias/activation only, 1 = gate and/or residual operands, 2 = fused AR q/k/v epilogue
 template <int BN, int EPI>
@@ -343,126 +468,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
 #pragma unroll 1
-      for (int c = half; c < n_chunks; c += 2) {
-        const int col0 = col_base + c * 32;
-        const bool live = row_ok && col0 < p.N;
-        const bool full = p.vec_ok && (col0 + 32 <= p.N);
-        // operand loads of this chunk go out before the accumulator read (independent of it)
-        uint4 gpre[4];
-        float4 rpre[8];
-        const bool pre_g = EPI == 1 && live && full && gate_bf, pre_r = EPI == 1 && live && full && p.resid != nullptr;
-        if (pre_g) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) gpre[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gate) + g_off + col0) + j);
-        }
-        if (pre_r) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rpre[j] = *(reinterpret_cast<const float4*>(p.resid + r_off + col0) + j);
-        }
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-        if (!live) continue;
-        // ---- bias
-        if (bias) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
-          }
-        }
-        // ---- activation (switch hoisted out of the element loop; fast-math variants: outputs are rounded to bf16)
-        switch (p.act) {
-          case ACT_GELU_ERF:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-            break;
-          case ACT_GELU_TANH:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
-            break;
-          case ACT_LEAKY02:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-            break;
-          case ACT_SILU:
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
-            break;
-          default: break;
-        }
-        if (full) {
-          if (pre_g) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t w[4] = {gpre[j].x, gpre[j].y, gpre[j].z, gpre[j].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                v[j * 8 + e * 2] *= __low2float(h); v[j * 8 + e * 2 + 1] *= __high2float(h);
-              }
-            }
-          } else if (EPI == 1 && p.gate) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float gv[4];
-              if (p.gate_dt == DT_F32) load4(reinterpret_cast<const float*>(p.gate) + g_off + col0 + j, gv);
-              else load4(reinterpret_cast<const bf16*>(p.gate) + g_off + col0 + j, gv);
-              v[j] *= gv[0]; v[j + 1] *= gv[1]; v[j + 2] *= gv[2]; v[j + 3] *= gv[3];
-            }
-          }
-          if (pre_r) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[j * 4] += rpre[j].x; v[j * 4 + 1] += rpre[j].y; v[j * 4 + 2] += rpre[j].z; v[j * 4 + 3] += rpre[j].w;
-            }
-          }
-          if (p.out32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.out32 + c_off + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-          if (p.out_act) {
-            if (p.out_act_dt == DT_F32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + c_off + col0 + j) =
-                    make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_act) + c_off + col0 + j) = pk;
-              }
-            }
-          }
-        } else {
-          // ragged / unaligned tail: fully unrolled with compile-time indices so v[] stays in registers
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.N) {
-              float t = v[j];
-              if (EPI == 1 && p.gate)
-                t *= (p.gate_dt == DT_F32) ? reinterpret_cast<const float*>(p.gate)[g_off + col0 + j]
-                                           : __bfloat162float(reinterpret_cast<const bf16*>(p.gate)[g_off + col0 + j]);
-              if (EPI == 1 && p.resid) t += p.resid[r_off + col0 + j];
-              if (p.out32) p.out32[c_off + col0 + j] = t;
-              if (p.out_act) {
-                if (p.out_act_dt == DT_F32) reinterpret_cast<float*>(p.out_act)[c_off + col0 + j] = t;
-                else reinterpret_cast<bf16*>(p.out_act)[c_off + col0 + j] = __float2bfloat16_rn(t);
-              }
-            }
-          }
-        }
-      }
+      for (int c = half; c < n_chunks; c += 2)
+        epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, bias,
+                       col_base + c * 32, gate_bf);
       }
       tc_fence_before();
       __syncwarp();
@@ -475,6 +483,193 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- CTA-pair kernel (cta_group::2)
+// Large GEMMs: a 128x256 tile per SM needs 48 KB of operands per 64-wide k-block; at the MMA rate that is more shared
+// memory traffic (TMA writes + MMA reads) than one SM sustains, which caps the 1-CTA kernel near 50-70 % tensor activity.
+// Here two CTAs of a cluster (one TPC) share a 256x256 tile: each loads its own 128 rows of A and HALF of the W tile
+// (32 KB per k-block per SM), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads both halves of W from
+// the two shared memories, and each CTA gets its 128 accumulator rows in its own TMEM for the epilogue.
+// Barriers: full[s] lives in the leader (both producers arrive, both CTAs' TMA bytes complete on it); empty[s] / tmem_full
+// are signalled in both CTAs by multicast commits; tmem_empty lives in the leader (16 epilogue warps arrive).
+constexpr int STAGES2 = 6;
+constexpr int STAGE2_BYTES = 2 * A_STAGE_BYTES;                 // per CTA: A 128x64 + W 128x64 (bf16)
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release.cta): an explicit .release.cluster compiles to MEMBAR.ALL.GPU + error barriers, ~1 us per
+  // arrive, which serialised the peer's producer once per k-block (ncu: 27 % tensor activity). Ordering of the TMEM reads
+  // against the leader's next MMAs comes from tcgen05.fence::before_thread_sync, as in the 1-CTA kernel.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D = F32, A = B = BF16, both K-major, M = 256 (CTA pair), N = 256
+__host__ __device__ constexpr uint32_t make_idesc_2sm() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES2 + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+
+  const int n_clusters = (int)(gridDim.x >> 1), cluster_id = (int)(blockIdx.x >> 1);
+  auto decode = [&](int tile, int& n_idx, int& mt, int& b) {
+    n_idx = tile % p.n_tiles_n;
+    const int rest = tile / p.n_tiles_n;
+    mt = rest % p.tiles_per_batch;
+    b = rest / p.tiles_per_batch;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      pdl_wait();
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+        int n_idx, mt, b;
+        decode(tile, n_idx, mt, b);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 0x21);
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
+          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * STAGE2_BYTES);
+          else mbar_arrive_cluster(lead_full);
+          tma_load_3d_2sm(sa, &tmA, lead_full, kb * BK, mt * 256 + (int)rank * 128, b);
+          tma_load_3d_2sm(sb, &tmW, lead_full, kb * BK, n_idx * BN + (int)rank * 128, 0);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_2sm();
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u, p.err_flag, 0x22);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.err_flag, 0x23);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            tc_mma_bf16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit_2sm(empty_bar(stage));         // frees the slot in both CTAs once these MMAs have read it
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_2sm(tfull_bar(acc));             // accumulator ready for both CTAs' epilogues
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, 128 rows each) =====================
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+    const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
+    int it = 0;
+    pdl_wait();
+    for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
+      int n_idx, mt, b;
+      decode(tile, n_idx, mt, b);
+      const int acc = it & 1;
+      const int t_in_batch = mt * 256 + (int)rank * 128 + q * 32 + lane;
+      const bool row_ok = t_in_batch < p.rpb;
+      const int r = b * p.rpb + t_in_batch;
+      const int64_t c_off = row_ok ? p.c_map.off(r) : 0;
+      const int64_t g_off = (row_ok && p.gate) ? p.gate_map.off(r) : 0;
+      const int64_t r_off = (row_ok && p.resid) ? p.resid_map.off(r) : 0;
+      const int col_base = n_idx * BN;
+      if (EPI == 1 && row_ok && p.vec_ok) {
+        for (int c = half; c < BN / 32; c += 2) {
+          const int col0 = col_base + c * 32;
+          if (col0 + 32 > p.N) break;
+          if (gate_bf) prefetch_l2(reinterpret_cast<const bf16*>(p.gate) + g_off + col0);
+          if (p.resid) prefetch_l2(p.resid + r_off + col0);
+        }
+      }
+      mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 0x24);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2)
+        epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, p.bias,
+                       col_base + c * 32, gate_bf);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+    }
+  }
+  // ---- teardown: the peer's shared memory and the leader's barriers stay alive until both CTAs are done
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -542,7 +737,39 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
   return launch_bn_epi<BN, 0>(tmA, tmW, tmWt, p, st);
 }
 
+template <int EPI>
+int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t st) {
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    AT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    cudaLaunchConfig_t qc = {};
+    qc.gridDim = dim3(g_num_sms & ~1); qc.blockDim = dim3(384); qc.dynamicSmemBytes = SMEM2_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa; qc.numAttrs = 1;
+    int n = 0;
+    AT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<EPI>, &qc));
+    max_clusters = n > 0 ? n : 1;
+    if (getenv("ARTALK_DEBUG")) fprintf(stderr, "[artalk] gemm pair kernel EPI=%d: max active clusters %d (SMs %d)\n", EPI, n, g_num_sms);
+    if (max_clusters > g_num_sms / 2) max_clusters = g_num_sms / 2;
+  }
+  const int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
+  g_trace_dims[0] = p.rpb * p.n_batches; g_trace_dims[1] = p.N; g_trace_dims[2] = p.num_kb * BK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
+  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, p));
+  AT_LAUNCH_CHECK();
+  return AT_OK;
+}
+int g_pair_mode = 1;      // 0: never use the CTA-pair kernel (developer switch, ARTALK_GEMM_PAIR=0)
+
 }  // namespace
+
+void set_gemm_pair_mode(int on) { g_pair_mode = on; }
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AT_OK;
@@ -567,6 +794,39 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.n_batches = batched ? ceil_div(g.M, g.a_map.rpb) : 1;
   AT_REQUIRE(!batched || g.M % g.a_map.rpb == 0, "gemm_tc: M must be a multiple of the A view's rows per batch");
   p.tiles_per_batch = ceil_div(p.rpb, BM);
+  // CTA-pair kernel (256x256 tiles over two SMs) for the large plain GEMMs: >= 4 waves of pair tiles at >= 85 % wave efficiency
+  if (g_pair_mode && !g.tap_w && g.groups == 1 && !g.qkv_mode && g.N >= 256 && g.N % 128 == 0) {
+    const int tpb2 = ceil_div(p.rpb, 256), n_tiles_n2 = ceil_div(g.N, 256), n_cl = g_num_sms / 2;
+    const long tiles2 = (long)p.n_batches * tpb2 * n_tiles_n2;
+    const long waves2 = (tiles2 + n_cl - 1) / n_cl;
+    const double row_eff = (double)p.rpb / ((double)tpb2 * 256.0);
+    if (tiles2 >= 4L * n_cl && (double)tiles2 / (double)(waves2 * n_cl) >= 0.85 && row_eff >= 0.85 && tiles2 < (1L << 30)) {
+      p.tiles_per_batch = tpb2; p.n_tiles_n = n_tiles_n2; p.groups = 1; p.total_tiles = (int)tiles2;
+      p.main_tiles = p.total_tiles; p.tail_split = 1; p.tail_bn = 256;
+      p.num_kb = ceil_div(g.K, BK);
+      p.tap_mode = 0; p.tap_pad = 0; p.a_group_cols = 0;
+      p.c_gs = 0; p.bias_gs = 0; p.bias = g.bias; p.act = g.act;
+      p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
+      p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;
+      p.err_flag = g_err_flag;
+      p.qkv_mode = 0; p.qkv_C = 0; p.head_scale = nullptr; p.qbuf = nullptr; p.kcache = nullptr; p.vcache = nullptr;
+      p.kv_map = g.kv_map; p.kv_layer_stride = 0;
+      bool v = (g.c_map.rs % 8 == 0) && (g.c_map.bs % 8 == 0);
+      if (g.bias) v = v && (((uintptr_t)g.bias) % 16 == 0);
+      if (g.gate) v = v && (g.gate_map.rs % 8 == 0) && (g.gate_map.bs % 8 == 0) && (((uintptr_t)g.gate) % 16 == 0);
+      if (g.resid) v = v && (g.resid_map.rs % 4 == 0) && (g.resid_map.bs % 4 == 0) && (((uintptr_t)g.resid) % 16 == 0);
+      if (g.out32) v = v && (((uintptr_t)g.out32) % 16 == 0);
+      if (g.out_act) v = v && (((uintptr_t)g.out_act) % 16 == 0);
+      p.vec_ok = v ? 1 : 0;
+      CUtensorMap tmA2, tmW2;
+      const uint64_t a_s1 = (uint64_t)g.a_map.rs * 2;
+      const uint64_t a_s2 = batched ? (uint64_t)g.a_map.bs * 2 : (uint64_t)p.rpb * g.a_map.rs * 2;
+      AT_TRY(make_map_3d(&tmA2, g.A, (uint64_t)g.K, (uint64_t)p.rpb, (uint64_t)p.n_batches, a_s1, a_s2 ? a_s2 : 16, BK, 128));
+      AT_TRY(make_map_3d(&tmW2, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.ldw * 2, (uint64_t)g.N * g.ldw * 2, BK, 128));
+      if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, p, st);
+      return launch_pair_epi<0>(tmA2, tmW2, p, st);
+    }
+  }
   // N-tile choice: persistent CTAs on 148 SMs quantise badly for the recurrence's GEMMs (e.g. 50 x 3 tiles of 128x256 =
   // 1.01 waves). Cost model per candidate BN: full waves x time of a BN-wide tile + the ragged wave, whose tiles are cut
   // into column slices (down to 32 columns, 64 for the fused q/k/v epilogue) when that lets them run side by side.

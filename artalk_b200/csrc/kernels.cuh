@@ -64,6 +64,8 @@ static inline GemmArgs gemm_args() {
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 // bf16 tcgen05/TMEM GEMM fed by TMA (A and W bf16). gemm_tc.cu
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+// developer switch: 0 = never use the CTA-pair (cta_group::2) kernel for large GEMMs
+void set_gemm_pair_mode(int on);
 
 // ---------------- attention.cu ----------------
 struct AttnArgs {

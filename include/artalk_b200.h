@@ -137,6 +137,9 @@ unsigned long long artalk_launch_count(void);
  * a kernel's prologue (barrier init, TMEM allocation, weight prefetch) overlaps the tail of its predecessor; 0 = plain
  * stream order. Process-wide; takes effect for launches (and CUDA-graph captures) made after the call. */
 int artalk_enable_pdl(int enable);
+/* process-wide tuning switches (developer / A-B measurement): "pdl" (0/1), "gemm_pair" (0 = never use the CTA-pair
+ * cta_group::2 GEMM kernel). Unknown names return an error. */
+int artalk_set_option(const char* name, int value);
 /* launch trace: between begin and end every kernel launch of the library records a CUDA event on its stream;
  * artalk_trace_end synchronises and writes "launcher,d0,d1,d2,microseconds" lines (time since the previous launch's
  * completion) into host_buf; returns the byte count (a value >= cap means the buffer was too small), -1 on error */

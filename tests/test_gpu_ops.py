@@ -65,6 +65,33 @@ def test_gemm_bias_act(pname, prec, dt, tol, M, N, K, act):
     assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K,act,resid", [(9472, 2048, 256, 1, False), (9400, 1024, 512, 0, True), (18944, 1280, 192, 2, True)])
+def test_gemm_cta_pair_kernel(M, N, K, act, resid):
+    """Large plain GEMMs take the cta_group::2 kernel (256x256 tiles over two SMs): same results as the fp64 reference,
+    including a ragged last M tile, a ragged N tile (1280 = 5 x 256), gate + in-place residual and dual outputs."""
+    dt, tol = torch.bfloat16, 3e-2
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).to(dev(), dt)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev(), dt)
+    b = torch.randn(N, generator=g).to(dev())
+    if resid:
+        x = torch.randn(M, N, generator=g).to(dev())
+        gate = torch.randn(M, N, generator=g).to(dev(), dt)
+        x0 = x.clone()
+        xa = torch.empty(M, N, device=dev(), dtype=dt)
+        run_gemm(1, A, W, M, N, K, bias=b, act=act, gate=gate, resid=x, out32=x, out_act=xa)
+        ref = (x0.double() + ACTS[act](A.double() @ W.double().t() + b.double()) * gate.double()).float()
+        scale = max(1.0, ref.abs().max().item())
+        assert (x - ref).abs().max().item() < tol * scale
+        assert (xa.float() - ref).abs().max().item() < (tol + 8e-3) * scale
+    else:
+        out = torch.full((M, N), float("nan"), device=dev(), dtype=dt)
+        run_gemm(1, A, W, M, N, K, bias=b, act=act, out_act=out)
+        ref = ACTS[act](A.double() @ W.double().t() + b.double()).float()
+        assert torch.isfinite(out.float()).all()
+        assert (out.float() - ref).abs().max().item() < (tol + 8e-3) * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("pname,prec,dt,tol", precisions())
 def test_gemm_gate_residual_rowmaps(pname, prec, dt, tol):
     """AR epilogue: x += (A W^T + b) * gamma with gamma rows gathered through (clip, token) maps; dual outputs."""
