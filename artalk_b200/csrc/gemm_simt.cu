@@ -1,13 +1,14 @@
 // fp32 CUDA-core GEMM with the path's fused epilogues:  out = resid + gate * act(A W^T + bias).
 // This is the arithmetic of the fp32 precision mode (north-star tolerance 1e-3) and of the tiny once-per-clip
 // style encoder; the bf16 mode runs the same GemmArgs through the tcgen05 kernel in gemm_tc.cu.
-// 128x128x16 tiles, 256 threads, 8x8 register tile per thread, register-prefetched double buffering.
+// 128x128x16 tiles, 256 threads, 8x8 register tile per thread, register-prefetched double buffering; a 32x128 variant
+// (2x8 per thread) keeps the small GEMMs of the style encoder (M = 50 rows per clip) from running on a handful of SMs.
 #include "kernels.cuh"
 
 namespace artalk {
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 16, PADM = 4;
+constexpr int BN = 128, BK = 16, PADM = 4;
 
 struct SimtParams {
   const float* A; RowMap a_map; const float* W; int64_t ldw; int M, N, K;
@@ -23,8 +24,10 @@ __device__ __forceinline__ float gate_at(const void* gate, int dt, int64_t off) 
   return dt == DT_F32 ? reinterpret_cast<const float*>(gate)[off] : __bfloat162float(reinterpret_cast<const bf16*>(gate)[off]);
 }
 
+template <int TM>          // rows per thread: 8 -> 128-row tiles, 2 -> 32-row tiles
 __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
   pdl_enter();
+  constexpr int BM = 16 * TM, AR = (BM + 63) / 64;      // AR: A rows fetched per loader thread
   __shared__ __align__(16) float As[2][BK][BM + PADM];
   __shared__ __align__(16) float Bs[2][BK][BN + PADM];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     int r = m0 + lr + 64 * i;
-    a_ok[i] = r < p.M;
+    a_ok[i] = i < AR && lr + 64 * i < BM && r < p.M;
     int rr = a_ok[i] ? r : 0;
     if (p.tap_w > 0) {
       int b = rr / p.a_map.rpb;
@@ -80,14 +83,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       int r = lr + 64 * i;
-      As[buf][lk + 0][r] = ra[i].x; As[buf][lk + 1][r] = ra[i].y; As[buf][lk + 2][r] = ra[i].z; As[buf][lk + 3][r] = ra[i].w;
+      if (r < BM) { As[buf][lk + 0][r] = ra[i].x; As[buf][lk + 1][r] = ra[i].y; As[buf][lk + 2][r] = ra[i].z; As[buf][lk + 3][r] = ra[i].w; }
       Bs[buf][lk + 0][r] = rb[i].x; Bs[buf][lk + 1][r] = rb[i].y; Bs[buf][lk + 2][r] = rb[i].z; Bs[buf][lk + 3][r] = rb[i].w;
     }
   };
 
-  float acc[8][8];
+  float acc[TM][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
@@ -100,14 +103,20 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
     if (kt + 1 < nk) fetch((kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float a[TM];
+      if constexpr (TM == 8) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      } else {
+        float2 a0 = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
+        a[0] = a0.x; a[1] = a0.y;
+      }
       float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
       float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
@@ -121,8 +130,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
   const float* bias = p.bias ? p.bias + g * p.bias_gs : nullptr;
   const int64_t cg = g * p.c_gs;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+  for (int i = 0; i < TM; ++i) {
+    int r = TM == 8 ? m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4)) : m0 + ty * 2 + i;
     if (r >= p.M) continue;
     int64_t c_off = p.c_map.off(r) + cg;
     int64_t g_off = p.gate ? p.gate_map.off(r) + cg : 0;
@@ -193,9 +202,15 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
   if (g.out32) v = v && (((uintptr_t)g.out32) % 16 == 0);
   if (g.out_act) v = v && (((uintptr_t)g.out_act) % 16 == 0);
   p.vec_ok = v ? 1 : 0;
-  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), g.groups);
   g_trace_dims[0] = g.M; g_trace_dims[1] = g.N; g_trace_dims[2] = g.K * g.groups;
-  AT_CUDA(launch_k(gemm_simt_kernel, dim3(grid), dim3(256), 0, st, p));
+  // less than one wave of 128-row tiles (148 SMs): 32-row tiles put 4x as many CTAs on the machine
+  if ((long)ceil_div(g.N, BN) * ceil_div(g.M, 128) * g.groups < 148) {
+    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, 32), g.groups);
+    AT_CUDA(launch_k(gemm_simt_kernel<2>, dim3(grid), dim3(256), 0, st, p));
+  } else {
+    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, 128), g.groups);
+    AT_CUDA(launch_k(gemm_simt_kernel<8>, dim3(grid), dim3(256), 0, st, p));
+  }
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

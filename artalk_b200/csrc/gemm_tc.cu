@@ -536,14 +536,15 @@ __device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// D = F32, A = B = BF16, both K-major, M = 256 (CTA pair), N = 256
-__host__ __device__ constexpr uint32_t make_idesc_2sm() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+// D = F32, A = B = BF16, both K-major, M = 256 (CTA pair), N = n
+__host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ CUtensorMap tmWt, const TcParams p) {
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -577,11 +578,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   pdl_launch_dependents();
 
   const int n_clusters = (int)(gridDim.x >> 1), cluster_id = (int)(blockIdx.x >> 1);
-  auto decode = [&](int tile, int& n_idx, int& mt, int& b) {
-    n_idx = tile % p.n_tiles_n;
-    const int rest = tile / p.n_tiles_n;
+  // tiles past main_tiles are column slices (tail_bn wide) of the ragged last wave's tiles
+  auto decode = [&](int tile, int& col_base, int& bn, int& mt, int& b) {
+    int big = tile, sub = 0;
+    bn = BN;
+    if (tile >= p.main_tiles) {
+      const int u = tile - p.main_tiles;
+      big = p.main_tiles + u / p.tail_split;
+      sub = u - (u / p.tail_split) * p.tail_split;
+      bn = p.tail_bn;
+    }
+    const int n_idx = big % p.n_tiles_n;
+    const int rest = big / p.n_tiles_n;
     mt = rest % p.tiles_per_batch;
     b = rest / p.tiles_per_batch;
+    col_base = n_idx * BN + sub * p.tail_bn;
   };
 
   if (warp == 0) {
@@ -590,16 +601,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       pdl_wait();
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
-        int n_idx, mt, b;
-        decode(tile, n_idx, mt, b);
+        int col_base, bn, mt, b;
+        decode(tile, col_base, bn, mt, b);
+        const int w_rows = bn >> 1;                     // this CTA's half of the W tile
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 0x21);
           const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
           const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * STAGE2_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * (uint32_t)(A_STAGE_BYTES + w_rows * BK * 2));
           else mbar_arrive_cluster(lead_full);
           tma_load_3d_2sm(sa, &tmA, lead_full, kb * BK, mt * 256 + (int)rank * 128, b);
-          tma_load_3d_2sm(sb, &tmW, lead_full, kb * BK, n_idx * BN + (int)rank * 128, 0);
+          tma_load_3d_2sm(sb, bn == BN ? &tmW : &tmWt, lead_full, kb * BK, col_base + (int)rank * w_rows, 0);
           if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
         }
       }
@@ -607,9 +619,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_2sm();
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
+        const uint32_t idesc = make_idesc_2sm(tile >= p.main_tiles ? p.tail_bn : BN);
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u, p.err_flag, 0x22);
         tc_fence_after();
@@ -635,8 +647,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int it = 0;
     pdl_wait();
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
-      int n_idx, mt, b;
-      decode(tile, n_idx, mt, b);
+      int col_base, bn, mt, b;
+      decode(tile, col_base, bn, mt, b);
+      const int n_chunks = bn >> 5;
       const int acc = it & 1;
       const int t_in_batch = mt * 256 + (int)rank * 128 + q * 32 + lane;
       const bool row_ok = t_in_batch < p.rpb;
@@ -644,9 +657,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int64_t c_off = row_ok ? p.c_map.off(r) : 0;
       const int64_t g_off = (row_ok && p.gate) ? p.gate_map.off(r) : 0;
       const int64_t r_off = (row_ok && p.resid) ? p.resid_map.off(r) : 0;
-      const int col_base = n_idx * BN;
       if (EPI == 1 && row_ok && p.vec_ok) {
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < n_chunks; c += 2) {
           const int col0 = col_base + c * 32;
           if (col0 + 32 > p.N) break;
           if (gate_bf) prefetch_l2(reinterpret_cast<const bf16*>(p.gate) + g_off + col0);
@@ -656,7 +668,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 0x24);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2)
+      for (int c = half; c < n_chunks; c += 2)
         epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, p.bias,
                        col_base + c * 32, gate_bf);
       tc_fence_before();
@@ -738,7 +750,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
 }
 
 template <int EPI>
-int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcParams& p, cudaStream_t st) {
+int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const TcParams& p, cudaStream_t st) {
   static int max_clusters = -1;
   if (max_clusters < 0) {
     AT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -761,7 +773,7 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcPara
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
-  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, p));
+  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, tmWt, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -798,11 +810,16 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g_pair_mode && !g.tap_w && g.groups == 1 && !g.qkv_mode && g.N >= 256 && g.N % 128 == 0) {
     const int tpb2 = ceil_div(p.rpb, 256), n_tiles_n2 = ceil_div(g.N, 256), n_cl = g_num_sms / 2;
     const long tiles2 = (long)p.n_batches * tpb2 * n_tiles_n2;
-    const long waves2 = (tiles2 + n_cl - 1) / n_cl;
     const double row_eff = (double)p.rpb / ((double)tpb2 * 256.0);
-    if (tiles2 >= 4L * n_cl && (double)tiles2 / (double)(waves2 * n_cl) >= 0.85 && row_eff >= 0.85 && tiles2 < (1L << 30)) {
-      p.tiles_per_batch = tpb2; p.n_tiles_n = n_tiles_n2; p.groups = 1; p.total_tiles = (int)tiles2;
-      p.main_tiles = p.total_tiles; p.tail_split = 1; p.tail_bn = 256;
+    // ragged last wave: its tiles are cut into column slices (>= 32 wide) that run side by side on the idle CTA pairs
+    const int rem2 = (int)(tiles2 % n_cl);
+    int split2 = 1;
+    if (rem2 > 0) while (256 / (split2 * 2) >= 32 && rem2 * split2 * 2 <= n_cl) split2 *= 2;
+    const double waves_eff = (double)(tiles2 / n_cl) + (rem2 ? (split2 > 1 ? 1.3 / split2 : 1.0) : 0.0);
+    if (tiles2 >= 4L * n_cl && (double)tiles2 / (waves_eff * n_cl) >= 0.85 && row_eff >= 0.85 && tiles2 < (1L << 30)) {
+      p.tiles_per_batch = tpb2; p.n_tiles_n = n_tiles_n2; p.groups = 1;
+      p.main_tiles = (int)tiles2 - (split2 > 1 ? rem2 : 0); p.tail_split = split2; p.tail_bn = 256 / split2;
+      p.total_tiles = p.main_tiles + (split2 > 1 ? rem2 * split2 : 0);
       p.num_kb = ceil_div(g.K, BK);
       p.tap_mode = 0; p.tap_pad = 0; p.a_group_cols = 0;
       p.c_gs = 0; p.bias_gs = 0; p.bias = g.bias; p.act = g.act;
@@ -823,8 +840,12 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
       const uint64_t a_s2 = batched ? (uint64_t)g.a_map.bs * 2 : (uint64_t)p.rpb * g.a_map.rs * 2;
       AT_TRY(make_map_3d(&tmA2, g.A, (uint64_t)g.K, (uint64_t)p.rpb, (uint64_t)p.n_batches, a_s1, a_s2 ? a_s2 : 16, BK, 128));
       AT_TRY(make_map_3d(&tmW2, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.ldw * 2, (uint64_t)g.N * g.ldw * 2, BK, 128));
-      if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, p, st);
-      return launch_pair_epi<0>(tmA2, tmW2, p, st);
+      CUtensorMap tmW2t = tmW2;
+      if (p.tail_split > 1)
+        AT_TRY(make_map_3d(&tmW2t, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.ldw * 2, (uint64_t)g.N * g.ldw * 2, BK,
+                           (uint32_t)(p.tail_bn / 2)));
+      if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, tmW2t, p, st);
+      return launch_pair_epi<0>(tmA2, tmW2, tmW2t, p, st);
     }
   }
   // N-tile choice: persistent CTAs on 148 SMs quantise badly for the recurrence's GEMMs (e.g. 50 x 3 tiles of 128x256 =
