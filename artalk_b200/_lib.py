@@ -95,6 +95,8 @@ SYMBOLS = {
                                         C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "artalk_set_savgol_tables": (C.c_int, [C.c_void_p, C.c_void_p]),
     "artalk_smooth_motion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "artalk_resample_mono": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_int64, C.c_void_p]),
     "artalk_launch_count": (C.c_ulonglong, []),
     "artalk_enable_pdl": (C.c_int, [C.c_int]),
     "artalk_set_option": (C.c_int, [C.c_char_p, C.c_int]),
@@ -124,6 +126,8 @@ def lib() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         if os.environ.get("ARTALK_PDL", "1") == "0":      # developer switch: plain stream-order launches
             l.artalk_enable_pdl(0)
+        if os.environ.get("ARTALK_ATTN_SIMT_MAX_LQ"):
+            l.artalk_set_option(b"attn_simt_max_lq", int(os.environ["ARTALK_ATTN_SIMT_MAX_LQ"]))
         if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":
             l.artalk_set_option(b"gemm_pair", 0)
         _lib = l

@@ -133,12 +133,18 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
   return launch_savgol_post(motion, out, n_clips, n_frames, n_frames_out, 106, fix_pose, zero_tail, (cudaStream_t)stream);
 }
 
+int artalk_resample_mono(const float* in, int channels, int64_t ch_stride, int64_t length, const float* bank, int orig, int new_f,
+                         int taps, int width, float* out, int64_t out_len, void* stream) {
+  return launch_resample_mix(in, channels, ch_stride, length, bank, orig, new_f, taps, width, out, out_len, (cudaStream_t)stream);
+}
+
 unsigned long long artalk_launch_count(void) { return g_launch_count; }
 int artalk_enable_pdl(int enable) { g_pdl = enable != 0; return AT_OK; }
 int artalk_set_option(const char* name, int value) {
   AT_REQUIRE(name, "artalk_set_option: null name");
   if (!std::strcmp(name, "pdl")) { g_pdl = value != 0; return AT_OK; }
   if (!std::strcmp(name, "gemm_pair")) { set_gemm_pair_mode(value); return AT_OK; }
+  if (!std::strcmp(name, "attn_simt_max_lq")) { set_attn_simt_max_lq(value); return AT_OK; }
   set_last_error("artalk_set_option: unknown option '%s'", name);
   return AT_EINVAL;
 }

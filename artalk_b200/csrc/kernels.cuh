@@ -82,6 +82,7 @@ struct AttnArgs {
 // dispatch: bf16 / head_dim 64 / <= 384 keys -> tcgen05 kernel (attention_tc.cu), otherwise the fp32-arithmetic SIMT kernel
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 bool attention_tc_supported(const AttnArgs& a);
+void set_attn_simt_max_lq(int v);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 // AR q/k/v post-processing (app/transformer.py:71-74): per-head L2 normalise q (x exp(min(scale_mul, ln100))) and k,
 // q -> qbuf [M, C]; k,v -> cache rows given by kv_map. qkv: [M, 3C] (q | k | v), or [M, 2C] (k | v) when has_q = 0.
@@ -142,5 +143,11 @@ size_t flame_workspace_floats(const FlameModel& fm, int n_frames);
 // Savitzky-Golay (win 5/poly 2; dims 100:103 win 9/poly 3, mode 'interp') + clip + pose/eye zeroing (inference.py:52-56,89-95)
 int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int T_out, int dim, int fix_pose,
                        int zero_tail, cudaStream_t st);
+
+// ---------------- frontend.cu ----------------
+// torchaudio-style polyphase sinc resampling + channel mean (inference.py:112-113,230-231): in [channels][length] (channel
+// stride ch_stride), bank [new][taps] with taps = 2*width + orig, out [out_len <= ceil(new*length/orig)]
+int launch_resample_mix(const float* in, int channels, int64_t ch_stride, int64_t length, const float* bank, int orig, int new_f,
+                        int taps, int width, float* out, int64_t out_len, cudaStream_t st);
 
 }  // namespace artalk

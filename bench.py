@@ -111,6 +111,9 @@ def main():
     ap.add_argument("--config", default="FULL", choices=["FULL", "TINY"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=1, help="independent clip lanes (streams) per GPU")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="profiling aid: run only the warm-up and timed resident steps (no e2e / instrumented / CPU legs), "
+                         "so an ncu launch list of the command covers whole steps and nothing else")
     args = ap.parse_args()
     cfg = getattr(config, args.config)
     n_samples = int(args.seconds * cfg.sample_rate)
@@ -201,6 +204,15 @@ def main():
     l0 = lib.artalk_launch_count()
     total_ms = timed(step_resident, args.steps, args.warmup)
     launches = (lib.artalk_launch_count() - l0) * args.steps // (args.steps + args.warmup)
+    if args.profile_step:
+        if sampler:
+            sampler.stop_flag.set(); sampler.join()
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": world * B * frames * args.steps / (total_ms / 1e3), "unit": "frames/s",
+                              "ms_per_step": total_ms / args.steps, "gpu_launches": int(launches), "profile_step": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_ms = timed(step_e2e, args.steps, 1)
     if sampler:
         sampler.stop_flag.set()
@@ -226,17 +238,18 @@ def main():
     gemm_tflops = fl_g / (ms_g * 1e-3) / 1e12 if ms_g > 0 else 0.0
     top_tflops = fl_top * n_top / (ms_top * 1e-3) / 1e12 if ms_top > 0 else 0.0
     peak = tf_sus if args.precision == "bf16" else 72.0
-    # ncu --set full capture of the dominant launch (profiles/r1c_ncu_full_summary.md): dram read + write per launch;
-    # only valid for the default workload's wav2vec FFN1 GEMM (M = clips*chunks*199 = 38208, N = 4096, K = 1024)
+    # ncu --set full capture of the dominant launches (profiles/r1g_ncu_full_summary.md): dram read + write per launch;
+    # only valid for the default workload's wav2vec FFN GEMMs (M = clips*chunks*199 = 38208, N x K = 4096 x 1024 / 1024 x 4096)
     is_default_top = args.precision == "bf16" and abs(fl_top - 2.0 * 38208 * 4096 * 1024) < 1.0
     roofline = {"bound": "tensor",
-                "kernel": ("gemm_tc_kernel<256> (tcgen05 bf16 GEMM), dominant shape of the step: %.1f GFLOP per launch, %d launches"
-                           % (fl_top / 1e9, int(n_top))) if args.precision == "bf16" else "gemm_simt_kernel (fp32 CUDA-core GEMM)",
+                "kernel": ("gemm_tc2_kernel (tcgen05 cta_group::2 bf16 GEMM, 256x256 tiles over CTA pairs), dominant shape of the "
+                           "step: %.1f GFLOP per launch, %d launches" % (fl_top / 1e9, int(n_top))) if args.precision == "bf16"
+                else "gemm_simt_kernel (fp32 CUDA-core GEMM)",
                 "achieved": top_tflops, "peak": peak, "unit": "TFLOP/s", "frac": top_tflops / peak,
-                "traffic": 475.2e6 if is_default_top else None,
+                "traffic": 492.0e6 if is_default_top else None,
                 "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the two wav2vec FFN GEMMs that "
                                 "share this flop count: FFN1 38208x4096x1024 86.9+259.9 MB (algorithmic 78 A + 8 W + 313 out), "
-                                "FFN2 38208x1024x4096 480.7+122.8 MB (algorithmic 313 A + 8 W + 157 resid read + 157 write)"
+                                "FFN2 38208x1024x4096 513.4+123.8 MB (algorithmic 313 A + 8 W + 157 resid read + 157 write)"
                 if is_default_top else None,
                 "peak_source": ("%s bf16_tflops_sustained (kernel timed inside a long step)" % src) if args.precision == "bf16"
                 else "nominal fp32 FMA peak 148 SMs x 128 lanes x 2 x 1.9 GHz",

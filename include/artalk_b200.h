@@ -126,6 +126,14 @@ int artalk_set_savgol_tables(const float* host_h5, const float* host_h9);
 int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_frames, int n_frames_out, int fix_pose,
                          int zero_tail, void* stream);
 
+/* Audio front-end of the callers (inference.py:112-113,230-231: torchaudio.transforms.Resample(sr, 16000)(audio).mean(dim=0)):
+ * polyphase windowed-sinc resampling fused with the channel mean. `in` is [channels][length] fp32 on the device (channel
+ * stride in elements), `bank` the [new][taps] filter bank of torchaudio's _get_sinc_resample_kernel for the gcd-reduced
+ * rates orig/new (taps = 2*width + orig; see artalk_b200/audio.py::sinc_resample_bank), `out` [out_len] with
+ * out_len <= ceil(new * length / orig). */
+int artalk_resample_mono(const float* in, int channels, int64_t ch_stride, int64_t length, const float* bank, int orig, int new_f,
+                         int taps, int width, float* out, int64_t out_len, void* stream);
+
 /* --- measurement hooks (bench.py) ---
  * artalk_launch_count: kernels launched by this library in this process so far.
  * artalk_profile_enable(e, 1): bracket every GEMM / attention launch of the engine with CUDA events on the launching
