@@ -92,6 +92,31 @@ class ARTAvatarInferEngine:
         clip_length = clip_length if clip_length is not None else self.clip_length
         return smooth_motion(pred, clip_length, self.fix_pose)
 
+    def inference_file(self, audio_path, clip_length=None):
+        """inference.py:230-235 for a WAV file: load, mix to mono, resample to 16 kHz on the device, run ``inference``."""
+        from .audio import load_audio
+        return self.inference(load_audio(audio_path, self.device), clip_length)
+
+    def save_motions(self, pred_motions, save_name):
+        """inference.py:124: ``torch.save(pred_motions.float().cpu(), <output_dir>/<save_name>_motions.pt)``; returns the path."""
+        path = os.path.join(self.output_dir, "{}_motions.pt".format(save_name))
+        os.makedirs(self.output_dir, exist_ok=True)
+        torch.save(pred_motions.float().cpu(), path)
+        return path
+
+    @staticmethod
+    def load_motions(path):
+        """(T,106) fp32 motion file written by the reference (inference.py:124) or by ``save_motions``."""
+        m = torch.load(path, map_location="cpu", weights_only=True)
+        if m.dim() != 2 or m.shape[1] != 106:
+            raise ValueError("expected a (T, 106) motion tensor, got {}".format(tuple(m.shape)))
+        return m.float()
+
+    def stream(self, batch=1):
+        """Streaming ingestion: audio arrives in pieces, every completed 4 s / 100-frame chunk is encoded and
+        decoded immediately with the AR state carried across chunks; see ``StreamingSession``."""
+        return StreamingSession(self, batch)
+
     def mesh_vertices(self, pred_motions, shape_code=None):
         """The vertices the mesh branch of ``rendering`` computes (inference.py:62-69): (N,106) -> (N,5023,3)."""
         if shape_code is None:
@@ -110,3 +135,83 @@ class ARTAvatarInferEngine:
     def smooth_motion_savgol(motion_codes):
         """inference.py:89-95 alone (no clipping / zeroing), on the device instead of the scipy host round trip."""
         return smooth_motion(motion_codes, None, False, zero_tail=False)
+
+
+class StreamingSession:
+    """Chunk-at-a-time form of ``ARTAvatarInferEngine.inference`` (app/models.py:76-115 run incrementally):
+
+        sess = engine.stream()
+        for piece in microphone:                 # (S_piece,) or (B, S_piece) fp32 16 kHz
+            for frames in sess.push(piece):      # (B, 100, 106) raw motion of every chunk completed by this piece
+                ...
+        tail = sess.flush()                      # last partial chunk (zero padded like app/models.py:79-80), trimmed to ceil(S/640)
+        motion = sess.result()                   # == engine.inference(all audio): smoothed, clipped, post-processed
+
+    The concatenated raw frames equal the whole-clip call bit for bit (same kernels on the same per-chunk operands); the
+    Savitzky-Golay post-filter needs neighbours on both sides, so smoothed output is only available from ``result()``.
+    """
+
+    def __init__(self, engine: ARTAvatarInferEngine, batch: int = 1):
+        self.engine, self.batch = engine, int(batch)
+        m = engine.ARTalk
+        self._cfg = m.cfg
+        style = engine.style_motion
+        if style is not None and style.shape[0] != self.batch:
+            style = style.expand(self.batch, -1, -1)
+        self._style = m.style_cond(style, self.batch)
+        self._prev = m.initial_words(self.batch)
+        self._buf = torch.empty(self.batch, 0, device=m.device)
+        self._frames = []
+        self._samples = 0
+        self._closed = False
+
+    def _run_chunk(self, chunk):
+        m = self.engine.ARTalk
+        cond = m.audio_cond(chunk)
+        out = torch.empty(self.batch, self._cfg.chunk_frames, self._cfg.motion_dim, device=m.device)
+        m.ar_chunk(cond, self._style, self._prev, out)
+        self._frames.append(out)
+        return out
+
+    def push(self, audio):
+        if self._closed:
+            raise RuntimeError("stream already flushed")
+        a = audio if audio.dim() == 2 else audio[None]
+        if a.shape[0] != self.batch:
+            raise ValueError("expected %d audio rows, got %d" % (self.batch, a.shape[0]))
+        a = a.to(self._buf.device, torch.float32)
+        self._samples += a.shape[1]
+        self._buf = torch.cat([self._buf, a], dim=1)
+        cs, done = self._cfg.chunk_samples, []
+        while self._buf.shape[1] >= cs:
+            done.append(self._run_chunk(self._buf[:, :cs].contiguous()))
+            self._buf = self._buf[:, cs:]
+        return done
+
+    def flush(self):
+        """Runs the zero-padded last chunk (if any audio is pending) and returns its useful frames (B, <=100, 106) or None."""
+        if self._closed:
+            return None
+        self._closed = True
+        total = self._cfg.frames_for_samples(self._samples)
+        have = len(self._frames) * self._cfg.chunk_frames
+        if self._buf.shape[1] == 0 or total <= have:
+            return None
+        pad = self._cfg.chunk_samples - self._buf.shape[1]
+        chunk = torch.cat([self._buf, self._buf.new_zeros(self.batch, pad)], dim=1)
+        out = self._run_chunk(chunk)
+        return out[:, :total - have]
+
+    def raw_motion(self):
+        """(B, ceil(S/640), 106) un-smoothed motion of everything pushed so far (app/models.py:115)."""
+        total = self._cfg.frames_for_samples(self._samples)
+        if not self._frames:
+            return torch.zeros(self.batch, 0, self._cfg.motion_dim, device=self._buf.device)
+        return torch.cat(self._frames, dim=1)[:, :total]
+
+    def result(self, clip_length=None):
+        """Smoothed / clipped / post-processed motion of the whole stream, as ``engine.inference`` returns it."""
+        self.flush()
+        clip_length = clip_length if clip_length is not None else self.engine.clip_length
+        out = smooth_motion(self.raw_motion(), clip_length, self.engine.fix_pose)
+        return out[0] if self.batch == 1 else out

@@ -295,3 +295,51 @@ def test_engine_surface_matches_reference_golden():
     np.testing.assert_allclose(verts[:3].cpu().numpy(), gv["verts"], atol=1e-3, rtol=0)
     with pytest.raises(NotImplementedError):
         eng.rendering(None, out)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_streaming_session_equals_whole_clip(precision, tmp_path):
+    """audio pushed in ragged pieces (chunk arrives -> encode -> AR) gives the whole-clip result; WAV file
+    ingestion (48 kHz stereo -> 16 kHz mono on the device) and the (T,106) .pt motion file round trip."""
+    import struct
+    import wave
+    from artalk_b200 import audio as fe
+    cfg = config.TINY
+    eng = ARTAvatarInferEngine(load_gaga=False, clip_length=750, device=DEV, precision=precision,
+                               state_dict=gu.state_dict("TINY"), config=cfg.to_reference_json(),
+                               flame_asset=synthetic.make_flame_asset(0), wav2vec=cfg.wav2vec, make_output_dir=False)
+    eng.output_dir = str(tmp_path)
+    eng.set_style_motion(synthetic.make_style_motion(1)[0])
+    S = 2 * cfg.chunk_samples + 12345                      # 2 full chunks + a ragged third
+    a = synthetic.make_audio(1, S)[0]
+    whole = eng.inference(a)
+    sess = eng.stream()
+    got, pos = [], 0
+    for piece in (1000, 70000, 3, 50000, S):               # ragged pieces, one spanning a chunk boundary
+        nxt = min(S, pos + piece)
+        got += sess.push(a[pos:nxt])
+        pos = nxt
+        if pos == S:
+            break
+    assert len(got) == 2 and all(tuple(g.shape) == (1, 100, 106) for g in got)
+    tail = sess.flush()
+    assert tail is not None and tail.shape[1] == cfg.frames_for_samples(S) - 200
+    out = sess.result()
+    assert out.shape == whole.shape
+    assert (out - whole).abs().max().item() < 1e-5
+    # motion file format of inference.py:124
+    path = eng.save_motions(out, "clip_natural_0_mesh")
+    back = ARTAvatarInferEngine.load_motions(path)
+    assert back.dtype == torch.float32 and torch.equal(back, out.float().cpu())
+    # WAV ingestion: 48 kHz stereo PCM16 -> same as resample_mono + inference
+    wav_path = str(tmp_path / "in.wav")
+    g = torch.Generator().manual_seed(5)
+    pcm = (0.1 * torch.randn(2, 48000 * 5, generator=g)).clamp(-1, 1)
+    ints = (pcm * 32767).round().to(torch.int16)
+    with wave.open(wav_path, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000)
+        w.writeframes(ints.t().contiguous().numpy().tobytes())
+    m_file = eng.inference_file(wav_path)
+    mono = fe.resample_mono(ints.float() / 32768.0, 48000, 16000, device=DEV)
+    assert mono.shape[0] == 16000 * 5
+    assert (m_file - eng.inference(mono)).abs().max().item() < 1e-5
