@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "engine.cuh"
 
@@ -626,6 +627,18 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
         use_graphs = false;                                          // fall back to eager launches for good
         if (rc != AT_OK) return rc;
       } else {
+        if (getenv("ARTALK_DEBUG")) {
+          size_t ne = 0;
+          if (cudaGraphGetEdges_v2(graph, nullptr, nullptr, nullptr, &ne) == cudaSuccess && ne > 0) {
+            std::vector<cudaGraphNode_t> from(ne), to(ne);
+            std::vector<cudaGraphEdgeData> ed(ne);
+            size_t prog = 0;
+            if (cudaGraphGetEdges_v2(graph, from.data(), to.data(), ed.data(), &ne) == cudaSuccess)
+              for (size_t i = 0; i < ne; ++i) prog += ed[i].type == cudaGraphDependencyTypeProgrammatic;
+            fprintf(stderr, "[artalk] captured chunk graph: %zu edges, %zu programmatic (PDL)\n", ne, prog);
+          }
+          cudaGetLastError();
+        }
         cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) { cudaGetLastError(); ge.exec = nullptr; use_graphs = false; }
