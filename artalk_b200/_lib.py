@@ -126,6 +126,10 @@ def lib() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         if os.environ.get("ARTALK_PDL", "1") == "0":      # developer switch: plain stream-order launches
             l.artalk_enable_pdl(0)
+        if os.environ.get("ARTALK_PDL_MASK"):
+            l.artalk_set_option(b"pdl_mask", int(os.environ["ARTALK_PDL_MASK"]))
+        if os.environ.get("ARTALK_PDL_W2V_MAX_CHUNKS"):
+            l.artalk_set_option(b"pdl_w2v_max_chunks", int(os.environ["ARTALK_PDL_W2V_MAX_CHUNKS"]))
         if os.environ.get("ARTALK_ATTN_SIMT_MAX_LQ"):
             l.artalk_set_option(b"attn_simt_max_lq", int(os.environ["ARTALK_ATTN_SIMT_MAX_LQ"]))
         if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":

@@ -143,6 +143,8 @@ int artalk_enable_pdl(int enable) { g_pdl = enable != 0; return AT_OK; }
 int artalk_set_option(const char* name, int value) {
   AT_REQUIRE(name, "artalk_set_option: null name");
   if (!std::strcmp(name, "pdl")) { g_pdl = value != 0; return AT_OK; }
+  if (!std::strcmp(name, "pdl_mask")) { g_pdl_mask = value; return AT_OK; }
+  if (!std::strcmp(name, "pdl_w2v_max_chunks")) { g_pdl_w2v_max_chunks = value; return AT_OK; }
   if (!std::strcmp(name, "gemm_pair")) { set_gemm_pair_mode(value); return AT_OK; }
   if (!std::strcmp(name, "attn_simt_max_lq")) { set_attn_simt_max_lq(value); return AT_OK; }
   set_last_error("artalk_set_option: unknown option '%s'", name);

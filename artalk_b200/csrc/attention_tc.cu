@@ -18,6 +18,7 @@
 // Persistent CTAs (grid = min(items, #SMs)). Masking: keys >= lk never contribute (TMA zero-fills them and P is forced to
 // 0); `split` implements the VAE's 2-block mask (app/modules/bitwise_vae.py:67-76). The KV-cached AR schedule needs no mask.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 / 8..11 = softmax + epilogue warpgroups 0 / 1.
+#define ARTALK_PDL_CLASS 2
 #include "kernels.cuh"
 #include "tc_ptx.cuh"
 

@@ -171,6 +171,12 @@ __device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 extern bool g_pdl;        // host switch (artalk_enable_pdl); default on
+extern int g_pdl_w2v_max_chunks;   // wav2vec sub-batches larger than this run without PDL (option "pdl_w2v_max_chunks")
+extern int g_pdl_mask;    // per kernel class (option "pdl_mask"): 1 = tcgen05 GEMM, 2 = tcgen05 attention, 4 = everything else
+#ifndef ARTALK_PDL_CLASS
+#define ARTALK_PDL_CLASS 4
+#endif
+static inline bool pdl_on() { return g_pdl && (g_pdl_mask & ARTALK_PDL_CLASS); }
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -178,7 +184,7 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = pdl_on() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -180,6 +180,8 @@ void* Engine::ws_alloc(size_t bytes) {
 
 unsigned long long g_launch_count = 0;
 bool g_pdl = true;
+int g_pdl_mask = 3;            // measured in the chunk graph: GEMM/attention edges help (-3.4 %), elementwise edges cancel it
+int g_pdl_w2v_max_chunks = 1 << 30;
 
 // ------------------------------------------------------------------ launch trace
 bool g_trace_on = false;
@@ -306,9 +308,10 @@ int Engine::audio_encode_sub(const float* audio, int n, float* cond, cudaStream_
   const int adt = act_dt();
   const size_t s = dt_size(adt);
   const int CD = c.w2v_conv_dim, H = c.w2v_hidden, F = n_audio_frames, M = n * F;
-  // programmatic dependent launch pays for the short launch-bound kernels of small batches; with hundreds of chunks in flight
-  // every kernel runs for >100 us at the power cap and early-resident dependents only cost (measured -4 % on 192 chunks)
-  struct PdlScope { bool saved; PdlScope(bool on) : saved(g_pdl) { g_pdl = g_pdl && on; } ~PdlScope() { g_pdl = saved; } } pdl_scope(n <= 16);
+  // programmatic dependent launch on every kernel class cost 4 % on a 192-chunk batch (elementwise kernels with 10^4 CTAs as
+  // early-resident dependents); with the class mask restricted to the tcgen05 kernels (g_pdl_mask = 3) it gains ~1.5 %, so the
+  // chunk-count cut-off is off by default and kept as an option
+  struct PdlScope { bool saved; PdlScope(bool on) : saved(g_pdl) { g_pdl = g_pdl && on; } ~PdlScope() { g_pdl = saved; } } pdl_scope(n <= g_pdl_w2v_max_chunks);
   WS(stats, float2*, (size_t)n * sizeof(float2));
   WS(bufA, char*, (size_t)n * std::max((size_t)conv_len[0] * CD, (size_t)F * std::max((size_t)c.w2v_ffn, (size_t)3 * H)) * s);
   WS(bufB, char*, (size_t)n * std::max((size_t)conv_len[1] * CD, (size_t)F * H) * s);

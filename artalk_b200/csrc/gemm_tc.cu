@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#define ARTALK_PDL_CLASS 1
 #include "kernels.cuh"
 
 namespace artalk {
@@ -772,7 +773,7 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_on() ? 2 : 1;
   AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, tmWt, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
