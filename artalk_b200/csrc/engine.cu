@@ -573,7 +573,7 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
   const int n_ada = NL * 6 * C + 2 * C, KV = 2 * L, Tm = T;
   const int64_t BL = (int64_t)B * L;
   size_t need = (size_t)BL * D * s + (size_t)BL * n_ada * s + (size_t)BL * C * s + (size_t)BL * NL * 2 * C * s +
-                2 * (size_t)NL * B * KV * C * s + (size_t)B * Tm * C * (4 + 3 * s) + (size_t)B * Tm * 4 * C * s +
+                2 * (size_t)NL * B * KV * C * s + (size_t)B * Tm * C * (8 + 3 * s) + (size_t)B * Tm * 4 * C * s +
                 (size_t)BL * 2 * c.code_dim * 4 + (size_t)BL * 4 * 3 + (size_t)B * C * 4 +
                 (size_t)B * Tm * (c.motion_dim + c.code_dim) * 4 +
                 (size_t)B * 2 * Tm * (c.code_dim * s + c.vae_hidden * (4 + s) + c.vae_hidden * s * 4 + c.vae_hidden * s * 3 / 2) +
@@ -691,6 +691,11 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
   WS(qbuf, char*, (size_t)B * Tm * C * s);
   WS(o, char*, (size_t)B * Tm * C * s);
   WS(f, char*, (size_t)B * Tm * 4 * C * s);
+  // bf16 mode: the projection / FFN2 GEMMs write y = A W^T + b (fp32) with the plain epilogue and the gated residual update
+  // x += gamma * y is folded into the next AdaLN kernel (bit-identical, see norms.cu); fp32 mode keeps the fused epilogue
+  const bool defer = (adt == DT_BF16);
+  float* ybuf = nullptr;
+  if (defer) { ybuf = (float*)ws_alloc((size_t)B * Tm * C * 4); if (!ybuf) return AT_ENOMEM; }
 
   // AdaLN parameters of every block + head for all 181 tokens, once per chunk (audio-only)
   GemmArgs g = gemm_args();
@@ -723,9 +728,11 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
     const uint32_t* src_words = forced_words ? forced_words : words;
     AT_TRY(launch_bits_tokens(tb, src_words, L, style, get<float>("ar.embed.w"), get<float>("ar.embed.b"), get<float>("ar.lvl_pos"), x,
                               DT_F32, B, p, p, C, st));
+    bool pending = false;                                    // ybuf holds the previous layer's FFN2 output, gate gamma2 of that layer
     for (int l = 0; l < NL; ++l) {
       const char* ada_l = ada_p + (size_t)l * 6 * C * s;     // chunk order: g1, g2, s1, s2, b1, b2 (quirk 9)
-      AT_TRY(launch_adaln_modulate(x, ada_l, adt, ada_map, 2 * C, 4 * C, u, adt, M, C, 1e-6f, st));
+      AT_TRY(launch_adaln_modulate(x, ada_l, adt, ada_map, 2 * C, 4 * C, u, adt, M, C, 1e-6f, st, pending ? ybuf : nullptr, -5 * C));
+      pending = false;
       g = gemm_args();
       g.A = u; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.qkv.w", l)); g.ldw = C; g.M = M; g.N = 3 * C; g.K = C;
       g.bias = get<float>(S("ar.l%d.qkv.b", l));
@@ -749,23 +756,25 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
       AT_TRY(attention(a, st));
       g = gemm_args();
       g.A = o; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.proj.w", l)); g.ldw = C; g.M = M; g.N = C; g.K = C;
-      g.bias = get<float>(S("ar.l%d.proj.b", l)); g.gate = ada_l; g.gate_dt = adt; g.gate_map = ada_map;       // gamma1
-      g.resid = x; g.resid_map = plain_rows(C); g.out32 = x; g.c_map = plain_rows(C);
+      g.bias = get<float>(S("ar.l%d.proj.b", l)); g.c_map = plain_rows(C);
+      if (defer) g.out32 = ybuf;
+      else { g.gate = ada_l; g.gate_dt = adt; g.gate_map = ada_map; g.resid = x; g.resid_map = plain_rows(C); g.out32 = x; }   // gamma1
       AT_TRY(gemm(g, st));
-      AT_TRY(launch_adaln_modulate(x, ada_l, adt, ada_map, 3 * C, 5 * C, u, adt, M, C, 1e-6f, st));
+      AT_TRY(launch_adaln_modulate(x, ada_l, adt, ada_map, 3 * C, 5 * C, u, adt, M, C, 1e-6f, st, defer ? ybuf : nullptr, 0));
       g = gemm_args();
       g.A = u; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.ff1.w", l)); g.ldw = C; g.M = M; g.N = 4 * C; g.K = C;
       g.bias = get<float>(S("ar.l%d.ff1.b", l)); g.act = ACT_GELU_TANH; g.out_act = f; g.out_act_dt = adt; g.c_map = plain_rows(4 * C);
       AT_TRY(gemm(g, st));
       g = gemm_args();
       g.A = f; g.a_map = plain_rows(4 * C); g.W = getw(S("ar.l%d.ff2.w", l)); g.ldw = 4 * C; g.M = M; g.N = C; g.K = 4 * C;
-      g.bias = get<float>(S("ar.l%d.ff2.b", l)); g.gate = ada_l + (size_t)C * s; g.gate_dt = adt; g.gate_map = ada_map;   // gamma2
-      g.resid = x; g.resid_map = plain_rows(C); g.out32 = x; g.c_map = plain_rows(C);
+      g.bias = get<float>(S("ar.l%d.ff2.b", l)); g.c_map = plain_rows(C);
+      if (defer) { g.out32 = ybuf; pending = true; }
+      else { g.gate = ada_l + (size_t)C * s; g.gate_dt = adt; g.gate_map = ada_map; g.resid = x; g.resid_map = plain_rows(C); g.out32 = x; }   // gamma2
       AT_TRY(gemm(g, st));
     }
     // head: AdaLN (scale, shift order) -> Linear 768 -> 64 -> pairwise argmax (app/models.py:103-104,145-148)
     const char* ada_h = ada_p + (size_t)NL * 6 * C * s;
-    AT_TRY(launch_adaln_modulate(x, ada_h, adt, ada_map, 0, C, u, adt, M, C, 1e-6f, st));
+    AT_TRY(launch_adaln_modulate(x, ada_h, adt, ada_map, 0, C, u, adt, M, C, 1e-6f, st, pending ? ybuf : nullptr, -5 * C));
     g = gemm_args();
     g.A = u; g.a_map = plain_rows(C); g.W = getw("ar.head.w"); g.ldw = C; g.M = M; g.N = 2 * c.code_dim; g.K = C;
     g.bias = get<float>("ar.head.b"); g.out32 = logits + (size_t)off * 2 * c.code_dim;

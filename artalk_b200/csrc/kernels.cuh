@@ -13,8 +13,11 @@ static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 int launch_layernorm(const float* x, int64_t x_rs, void* out, int out_dt, int64_t out_rs, const float* gamma,
                      const float* beta, int rows, int cols, float eps, int act, cudaStream_t st);
 // out[r] = LN_eps(x[r]) * (1 + ada[map(r)][scale_off + c]) + ada[map(r)][shift_off + c]   (app/transformer.py:35,40)
-int launch_adaln_modulate(const float* x, const void* ada, int ada_dt, RowMap ada_map, int scale_off, int shift_off,
-                          void* out, int out_dt, int rows, int cols, float eps, cudaStream_t st);
+// With y != null the row is first updated in place: x[r] <- fma(ada[map(r)][gate_off + c], y[r][c], x[r][c]) (the deferred
+// gated residual of the previous projection / FFN GEMM, y = [rows, cols] fp32).
+int launch_adaln_modulate(float* x, const void* ada, int ada_dt, RowMap ada_map, int scale_off, int shift_off,
+                          void* out, int out_dt, int rows, int cols, float eps, cudaStream_t st, const float* y = nullptr,
+                          int gate_off = 0);
 // stats[chunk] = (mean, 1/(std_unbiased + 1e-6))   (app/modules/wav2vec.py:23-27)
 int launch_audio_stats(const float* audio, int n_chunks, int n_samples, float2* stats, cudaStream_t st);
 // conv layer 0 (Cin=1,k=10,s=5) on normalised audio + LN(512) + GELU_erf, channels-last output [n, L_out, 512]

@@ -72,20 +72,35 @@ int launch_layernorm(const float* x, int64_t x_rs, void* out, int out_dt, int64_
 }
 
 // ---------------------------------------------------------------- AdaLN modulate
+// Optionally folds the previous sub-layer's gated residual update in first (app/transformer.py:37,41):
+//   x[r] <- fma(gate[r], y[r], x[r])   with y = the fp32 output of the projection / FFN GEMM, gate = ada[map(r)][gate_off + c]
+// so those GEMMs run with the plain epilogue (no gate / residual loads per output row) and the read-modify-write of the fp32
+// residual stream happens here, one warp per row with 16-byte accesses. Same arithmetic (one fma per element) as the fused
+// GEMM epilogue, so results are bit-identical.
 template <int V4, typename TA, typename TO>
-__global__ void __launch_bounds__(128) adaln_kernel(const float* __restrict__ x, const TA* __restrict__ ada, RowMap ada_map,
+__global__ void __launch_bounds__(128) adaln_kernel(float* __restrict__ x, const TA* __restrict__ ada, RowMap ada_map,
                                                     int scale_off, int shift_off, TO* __restrict__ out, int rows,
-                                                    float eps) {
+                                                    float eps, const float* __restrict__ y, int gate_off) {
   pdl_enter();
   constexpr int C = V4 * 128;
   int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* xr = x + (int64_t)row * C;
+  float* xr = x + (int64_t)row * C;
+  const TA* ar = ada + ada_map.off(row);
   float v[V4][4];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < V4; ++i) {
-    load4(xr + (i * 32 + lane) * 4, v[i]);
+    const int c = (i * 32 + lane) * 4;
+    load4(xr + c, v[i]);
+    if (y) {
+      float yv[4], gv[4];
+      load4(y + (int64_t)row * C + c, yv);
+      load4(ar + gate_off + c, gv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = fmaf(yv[j], gv[j], v[i][j]);
+      store4(xr + c, v[i]);
+    }
     s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
   }
   float mean = warp_sum(s) * (1.0f / C);
@@ -95,7 +110,6 @@ __global__ void __launch_bounds__(128) adaln_kernel(const float* __restrict__ x,
 #pragma unroll
     for (int j = 0; j < 4; ++j) { float d = v[i][j] - mean; q += d * d; }
   float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
-  const TA* ar = ada + ada_map.off(row);
   TO* orow = out + (int64_t)row * C;
 #pragma unroll
   for (int i = 0; i < V4; ++i) {
@@ -109,19 +123,19 @@ __global__ void __launch_bounds__(128) adaln_kernel(const float* __restrict__ x,
   }
 }
 
-int launch_adaln_modulate(const float* x, const void* ada, int ada_dt, RowMap ada_map, int scale_off, int shift_off,
-                          void* out, int out_dt, int rows, int cols, float eps, cudaStream_t st) {
+int launch_adaln_modulate(float* x, const void* ada, int ada_dt, RowMap ada_map, int scale_off, int shift_off,
+                          void* out, int out_dt, int rows, int cols, float eps, cudaStream_t st, const float* y, int gate_off) {
   if (rows <= 0) return AT_OK;
   AT_REQUIRE(cols == 768, "adaln: width must be 768 (got %d)", cols);
   dim3 grid(ceil_div(rows, 4));
   if (ada_dt == DT_F32 && out_dt == DT_F32)
-    AT_CUDA(launch_k(adaln_kernel<6, float, float>, dim3(grid), dim3(128), 0, st, x, (const float*)ada, ada_map, scale_off, shift_off, (float*)out, rows, eps));
+    AT_CUDA(launch_k(adaln_kernel<6, float, float>, dim3(grid), dim3(128), 0, st, x, (const float*)ada, ada_map, scale_off, shift_off, (float*)out, rows, eps, y, gate_off));
   else if (ada_dt == DT_BF16 && out_dt == DT_BF16)
-    AT_CUDA(launch_k(adaln_kernel<6, bf16, bf16>, dim3(grid), dim3(128), 0, st, x, (const bf16*)ada, ada_map, scale_off, shift_off, (bf16*)out, rows, eps));
+    AT_CUDA(launch_k(adaln_kernel<6, bf16, bf16>, dim3(grid), dim3(128), 0, st, x, (const bf16*)ada, ada_map, scale_off, shift_off, (bf16*)out, rows, eps, y, gate_off));
   else if (ada_dt == DT_F32 && out_dt == DT_BF16)
-    AT_CUDA(launch_k(adaln_kernel<6, float, bf16>, dim3(grid), dim3(128), 0, st, x, (const float*)ada, ada_map, scale_off, shift_off, (bf16*)out, rows, eps));
+    AT_CUDA(launch_k(adaln_kernel<6, float, bf16>, dim3(grid), dim3(128), 0, st, x, (const float*)ada, ada_map, scale_off, shift_off, (bf16*)out, rows, eps, y, gate_off));
   else
-    AT_CUDA(launch_k(adaln_kernel<6, bf16, float>, dim3(grid), dim3(128), 0, st, x, (const bf16*)ada, ada_map, scale_off, shift_off, (float*)out, rows, eps));
+    AT_CUDA(launch_k(adaln_kernel<6, bf16, float>, dim3(grid), dim3(128), 0, st, x, (const bf16*)ada, ada_map, scale_off, shift_off, (float*)out, rows, eps, y, gate_off));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
