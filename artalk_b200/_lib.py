@@ -97,6 +97,7 @@ SYMBOLS = {
     "artalk_smooth_motion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "artalk_resample_mono": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_int64, C.c_void_p]),
+    "artalk_ema_scan": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "artalk_launch_count": (C.c_ulonglong, []),
     "artalk_enable_pdl": (C.c_int, [C.c_int]),
     "artalk_set_option": (C.c_int, [C.c_char_p, C.c_int]),

@@ -138,6 +138,11 @@ int artalk_resample_mono(const float* in, int channels, int64_t ch_stride, int64
   return launch_resample_mix(in, channels, ch_stride, length, bank, orig, new_f, taps, width, out, out_len, (cudaStream_t)stream);
 }
 
+int artalk_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_idx, int n_frames, float* state, int has_state,
+                    float keep, void* stream) {
+  return launch_ema_scan(points, frame_stride, idx, n_idx, n_frames, state, has_state, keep, (cudaStream_t)stream);
+}
+
 unsigned long long artalk_launch_count(void) { return g_launch_count; }
 int artalk_enable_pdl(int enable) { g_pdl = enable != 0; return AT_OK; }
 int artalk_set_option(const char* name, int value) {

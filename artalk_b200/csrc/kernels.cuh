@@ -147,6 +147,10 @@ size_t flame_workspace_floats(const FlameModel& fm, int n_frames);
 int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int T_out, int dim, int fix_pose,
                        int zero_tail, cudaStream_t st);
 
+// forehead EMA scan of the GAGAvatar point builder (app/GAGAvatar/models.py:120-125): points [n_frames][V][3] updated in place
+int launch_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_idx, int n_frames, float* state, int has_state,
+                    float keep, cudaStream_t st);
+
 // ---------------- frontend.cu ----------------
 // torchaudio-style polyphase sinc resampling + channel mean (inference.py:112-113,230-231): in [channels][length] (channel
 // stride ch_stride), bank [new][taps] with taps = 2*width + orig, out [out_len <= ceil(new*length/orig)]

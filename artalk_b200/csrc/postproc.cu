@@ -59,4 +59,35 @@ int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int 
   return AT_OK;
 }
 
+// ---------------------------------------------------------------- forehead EMA of the GAGAvatar point builder
+// app/GAGAvatar/models.py:120-125, run frame by frame by the reference: the first frame ever initialises the state with its
+// own points, every later frame does u <- 0.98 u + 0.02 c and the frame's forehead vertices are REPLACED by u. Batched here
+// as a scan over the frames of one call: one thread per (forehead vertex, coordinate), sequential over frames (a first-order
+// IIR, <= 750 steps), state carried across calls in `state` [n_idx][3].
+__global__ void __launch_bounds__(128) ema_scan_kernel(float* __restrict__ points, int64_t frame_stride, const int* __restrict__ idx,
+                                                       int n_idx, int n_frames, float* __restrict__ state, int has_state, float keep) {
+  pdl_enter();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_idx * 3) return;
+  const int v = idx[t / 3], c = t % 3;
+  float* p = points + (int64_t)v * 3 + c;
+  float u = has_state ? state[t] : 0.f;
+  for (int f = 0; f < n_frames; ++f, p += frame_stride) {
+    const float cur = *p;
+    if (f == 0 && !has_state) u = cur;                       // models.py:120-121: no blending on the very first frame
+    else { u = keep * u + (1.0f - keep) * cur; *p = u; }     // models.py:123-125
+  }
+  state[t] = u;
+}
+
+int launch_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_idx, int n_frames, float* state, int has_state,
+                    float keep, cudaStream_t st) {
+  if (n_idx <= 0 || n_frames <= 0) return AT_OK;
+  AT_REQUIRE(points && idx && state && keep >= 0.f && keep <= 1.f, "ema_scan: bad argument");
+  AT_CUDA(launch_k(ema_scan_kernel, dim3(ceil_div(n_idx * 3, 128)), dim3(128), 0, st, points, frame_stride, idx, n_idx, n_frames, state,
+                   has_state, keep));
+  AT_LAUNCH_CHECK();
+  return AT_OK;
+}
+
 }  // namespace artalk

@@ -1,0 +1,52 @@
+"""FLAME side of ``GAGAvatar.build_forward_batch`` (app/GAGAvatar/models.py:98-128), the second consumer of the motion codes:
+FLAME decode with ``scale=5.0`` and the tracked avatar's shape code, jaw-only pose (``[0,0,0, motion[103:106]]``, zero eye
+pose), then the forehead vertices follow an EMA across frames. The reference runs this one frame at a time inside its
+render loop (inference.py:78-84); here a whole clip is decoded in one FLAME launch and the EMA is a device scan whose state
+carries across calls, so frame-by-frame and batched calls agree. The Gaussian rasteriser, the camera transform
+(``transform_emoca_to_p3d``, pytorch3d) and the image branches of the batch are rendering and stay out of scope.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .flame import FLAMEModel
+
+
+class GagaPointBuilder:
+    def __init__(self, flame_model: FLAMEModel, shapecode: torch.Tensor, forehead_indices, keep: float = 0.98):
+        """``flame_model`` built with ``scale=5.0`` (models.py:20), ``shapecode`` (1,300) of the tracked avatar,
+        ``forehead_indices`` the reference's vertex list (models.py:326)."""
+        if shapecode.dim() != 2 or shapecode.shape[0] != 1:
+            raise ValueError("shapecode must be (1, n_shape)")
+        self.flame = flame_model
+        self.device = flame_model.device
+        self.shapecode = shapecode.to(self.device, torch.float32)
+        self.idx = torch.as_tensor(list(forehead_indices), dtype=torch.int32, device=self.device)
+        if self.idx.numel() and (int(self.idx.min()) < 0 or int(self.idx.max()) >= flame_model.n_verts):
+            raise ValueError("forehead index out of range")
+        self.keep = float(keep)
+        self.state = torch.zeros(self.idx.numel(), 3, device=self.device)
+        self.has_state = False
+
+    def reset(self):
+        self.has_state = False
+
+    @torch.no_grad()
+    def t_points(self, motion_code: torch.Tensor) -> torch.Tensor:
+        """(N,106) motion codes of consecutive frames -> ``feature_batch['t_points']`` for each frame, (N,5023,3)."""
+        m = motion_code.to(self.device, torch.float32)
+        if m.dim() != 2 or m.shape[1] != 106:
+            raise ValueError("motion_code must be (N, 106)")
+        N = m.shape[0]
+        if N == 0:
+            return torch.zeros(0, self.flame.n_verts, 3, device=self.device)
+        exp_code = m[:, :100]
+        pose_code = torch.cat([m.new_zeros(N, 3), m[:, 103:]], dim=-1)                  # models.py:115
+        pts = self.flame(shape_params=self.shapecode.expand(N, -1), pose_params=pose_code, expression_params=exp_code,
+                         eye_pose_params=m.new_zeros(N, 6)).float()
+        if self.idx.numel():
+            _lib.check(_lib.lib().artalk_ema_scan(pts.data_ptr(), pts.stride(0), self.idx.data_ptr(), self.idx.numel(), N,
+                                                  self.state.data_ptr(), int(self.has_state), self.keep, _lib.stream_ptr(self.device)))
+        self.has_state = True
+        return pts

@@ -134,6 +134,13 @@ int artalk_smooth_motion(const float* motion, float* out, int n_clips, int n_fra
 int artalk_resample_mono(const float* in, int channels, int64_t ch_stride, int64_t length, const float* bank, int orig, int new_f,
                          int taps, int width, float* out, int64_t out_len, void* stream);
 
+/* Second FLAME consumer (app/GAGAvatar/models.py:98-128, build_forward_batch): after FLAME decode with scale 5.0 and the
+ * avatar's shape code, the forehead vertices follow an exponential moving average across frames (models.py:120-125). `points`
+ * is [n_frames][V][3] (frame stride in floats), `idx` the forehead vertex indices on the device, `state` [n_idx][3] carried
+ * across calls (has_state = 0 on the first call: the first frame initialises it unblended), keep = 0.98. In place. */
+int artalk_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_idx, int n_frames, float* state, int has_state,
+                    float keep, void* stream);
+
 /* --- measurement hooks (bench.py) ---
  * artalk_launch_count: kernels launched by this library in this process so far.
  * artalk_profile_enable(e, 1): bracket every GEMM / attention launch of the engine with CUDA events on the launching

@@ -362,3 +362,22 @@ def get_flame_verts(asset, shape_params, motion, with_global=False, scale=1.0):
     if not with_global:
         pose = torch.cat([torch.zeros_like(pose[..., :3]), pose[..., 3:]], dim=-1)
     return flame_vertices(asset, shape_params, expr, pose, scale=scale)
+
+
+def gaga_t_points(asset, shapecode, motion, forehead_indices, scale=5.0, keep=0.98):
+    """app/GAGAvatar/models.py:112-126 run frame by frame like the reference's render loop (inference.py:78-84):
+    FLAME(scale 5.0, avatar shape, pose [0,0,0,jaw], zero eye pose) then the forehead EMA. Parity unpinned: importing the
+    reference's GAGAvatar module needs torchvision / pytorch3d / the tracked-avatar assets, none of which exist here."""
+    idx = torch.as_tensor(list(forehead_indices), dtype=torch.long)
+    out, upper = [], None
+    for f in range(motion.shape[0]):
+        mc = motion[f:f + 1]
+        pose = torch.cat([mc.new_zeros(1, 3), mc[:, 103:]], dim=-1)
+        pts = flame_vertices(asset, shapecode, mc[:, :100], pose, scale=scale).float()
+        if upper is None:
+            upper = pts[:, idx].clone()
+        else:
+            upper = keep * upper + (1.0 - keep) * pts[:, idx]
+            pts[:, idx] = upper
+        out.append(pts[0])
+    return torch.stack(out, 0)

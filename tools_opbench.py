@@ -124,8 +124,8 @@ if a.only in ("", "gemm"):
     ar = 0.0
     for n_new in (1, 5, 25, 50, 100):
         M = B * n_new
-        for lab, args in [("ar qkv", dict(M=M, N=2304, K=768)), ("ar proj+gate+resid", dict(M=M, N=768, K=768, resid=True, gate=True, out="f32")),
-                          ("ar ff1 gelu", dict(M=M, N=3072, K=768, act=2)), ("ar ff2+gate+resid", dict(M=M, N=768, K=3072, resid=True, gate=True, out="f32"))]:
+        for lab, args in [("ar qkv", dict(M=M, N=2304, K=768)), ("ar proj (fp32 y)", dict(M=M, N=768, K=768, out="f32")),
+                          ("ar ff1 gelu", dict(M=M, N=3072, K=768, act=2)), ("ar ff2 (fp32 y)", dict(M=M, N=768, K=3072, out="f32"))]:
             if want(lab):
                 ar += 12 * NCH * bench_gemm("%s n=%d" % (lab, n_new), **args)
     print("  -> AR block GEMMs per step: %.2f ms" % (ar / 1e3))
