@@ -10,7 +10,7 @@ import torch
 from .config import ModelConfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libartalk_b200.so")
+LIB_PATH = os.environ.get("ARTALK_LIB") or os.path.join(HERE, "lib", "libartalk_b200.so")      # ARTALK_LIB: A/B builds
 
 F32, BF16, I32 = 0, 1, 2
 PRECISION = {"fp32": 0, "bf16": 1}
@@ -131,6 +131,8 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"pdl_mask", int(os.environ["ARTALK_PDL_MASK"]))
         if os.environ.get("ARTALK_PDL_W2V_MAX_CHUNKS"):
             l.artalk_set_option(b"pdl_w2v_max_chunks", int(os.environ["ARTALK_PDL_W2V_MAX_CHUNKS"]))
+        if os.environ.get("ARTALK_GEMM_FORCE_BN"):
+            l.artalk_set_option(b"gemm_force_bn", int(os.environ["ARTALK_GEMM_FORCE_BN"]))
         if os.environ.get("ARTALK_ATTN_SIMT_MAX_LQ"):
             l.artalk_set_option(b"attn_simt_max_lq", int(os.environ["ARTALK_ATTN_SIMT_MAX_LQ"]))
         if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":

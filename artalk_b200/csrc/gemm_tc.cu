@@ -150,31 +150,43 @@ template <int BN> struct TileCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue scratch*/;
 };
 
-// One 32-column chunk of one output row: out = resid + gate * act(acc + bias). The chunk's gate / residual loads are issued
-// ahead of the tcgen05.ld of the accumulator so both latencies overlap. Shared by the 1-CTA and the CTA-pair kernels.
+// One 32-column chunk of 32 output rows (one warp; thread = row, as tcgen05.ld delivers the accumulator):
+//   out = resid + gate * act(acc + bias).
+// Row-per-thread global accesses cost one L1 tag lookup per lane per instruction (32 different 128-byte lines for 16 bytes
+// each): 20 000 tag cycles per 128x256 tile with an fp32 residual read-modify-write and a bf16 copy, against 4 096-8 192 cycles
+// of MMA for K = 512-1024. So the fp32 residual comes in and the outputs go out through a per-warp 4 KB shared-memory
+// transposition (16-byte chunks XOR-swizzled with the row: conflict-free both ways): every global instruction of the warp
+// covers 4 full 128-byte lines (fp32) or 8 x 64 bytes (bf16). The loads are issued ahead of the tcgen05.ld of the accumulator.
+// Shared by the 1-CTA and the CTA-pair kernels. All 32 lanes must call it (shuffles, __syncwarp).
+constexpr int EPI_SCRATCH_BYTES = 8 * 4096;       // 8 epilogue warps x (32 rows x 128 B)
+
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, bool row_ok, int64_t c_off, int64_t g_off, int64_t r_off,
-                                          const float* bias, int col0, bool gate_bf) {
+                                          const float* bias, int col0, bool gate_bf, float4* scr, int lane) {
     const bool live = row_ok && col0 < p.N;
-    const bool full = p.vec_ok && (col0 + 32 <= p.N);
+    const bool full = p.vec_ok && (col0 + 32 <= p.N);            // warp-uniform
+    const int sw = lane & 7;
     // operand loads of this chunk go out before the accumulator read (independent of it)
     uint4 gpre[4];
     float4 rpre[8];
-    const bool pre_g = EPI == 1 && live && full && gate_bf, pre_r = EPI == 1 && live && full && p.resid != nullptr;
+    const bool pre_g = EPI == 1 && live && full && gate_bf;
+    const bool use_r = EPI == 1 && full && p.resid != nullptr;   // warp-uniform
     if (pre_g) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) gpre[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gate) + g_off + col0) + j);
     }
-    if (pre_r) {
+    if (use_r && live) {
+      // row-per-thread 16-byte loads, in flight while the accumulator is read (a transposed, coalesced variant of this load
+      // measured 50 % slower: it has to land in shared memory before the tcgen05.ld, which serialises the two latencies)
 #pragma unroll
       for (int j = 0; j < 8; ++j) rpre[j] = *(reinterpret_cast<const float4*>(p.resid + r_off + col0) + j);
     }
     float v[32];
     tmem_ld32(taddr, v);
-    if (!live) return;
+    if (!full && !live) return;                                  // ragged path below is per thread (no warp collectives)
     // ---- bias
     if (bias) {
       if (full) {
@@ -219,7 +231,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
             v[j * 8 + e * 2] *= __low2float(h); v[j * 8 + e * 2 + 1] *= __high2float(h);
           }
         }
-      } else if (EPI == 1 && p.gate) {
+      } else if (EPI == 1 && p.gate && live) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float gv[4];
@@ -228,35 +240,46 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
           v[j] *= gv[0]; v[j + 1] *= gv[1]; v[j + 2] *= gv[2]; v[j + 3] *= gv[3];
         }
       }
-      if (pre_r) {
+      if (use_r && live) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[j * 4] += rpre[j].x; v[j * 4 + 1] += rpre[j].y; v[j * 4 + 2] += rpre[j].z; v[j * 4 + 3] += rpre[j].w;
         }
       }
-      if (p.out32) {
+      // ---- outputs through the transposition: own row in, row-major 16-byte pieces out
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(p.out32 + c_off + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      }
-      if (p.out_act) {
-        if (p.out_act_dt == DT_F32) {
+      for (int ch = 0; ch < 8; ++ch) scr[lane * 8 + (ch ^ sw)] = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+      __syncwarp();
+      const bool act_f32 = p.out_act && p.out_act_dt == DT_F32, act_bf = p.out_act && p.out_act_dt != DT_F32;
+      if (p.out32 || act_f32) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + c_off + col0 + j) =
-                make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_act) + c_off + col0 + j) = pk;
+        for (int it = 0; it < 8; ++it) {
+          const int j = it * 4 + (lane >> 3), ch = lane & 7;
+          const int64_t off_j = __shfl_sync(0xffffffffu, c_off, j);
+          const bool ok_j = __shfl_sync(0xffffffffu, (int)row_ok, j) != 0;
+          const float4 o = scr[j * 8 + (ch ^ (j & 7))];
+          if (ok_j) {
+            if (p.out32) *reinterpret_cast<float4*>(p.out32 + off_j + col0 + ch * 4) = o;
+            if (act_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + off_j + col0 + ch * 4) = o;
           }
         }
       }
+      if (act_bf) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int j = it * 8 + (lane >> 2), c2 = lane & 3;          // 4 lanes x 16 B (8 bf16) per row
+          const int64_t off_j = __shfl_sync(0xffffffffu, c_off, j);
+          const bool ok_j = __shfl_sync(0xffffffffu, (int)row_ok, j) != 0;
+          const float4 a = scr[j * 8 + ((2 * c2) ^ (j & 7))], b = scr[j * 8 + ((2 * c2 + 1) ^ (j & 7))];
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          if (ok_j) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_act) + off_j + col0 + c2 * 8) = pk;
+        }
+      }
+      __syncwarp();                                              // the scratch may be overwritten by the next chunk
     } else {
       // ragged / unaligned tail: fully unrolled with compile-time indices so v[] stays in registers
 #pragma unroll
@@ -403,6 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // and always miss), and the chunk's loads are issued ahead of the tcgen05.ld so both latencies overlap.
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
+    float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)) + (warp - 4) * 4096);
     int it = 0;
     pdl_wait();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -471,7 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += 2)
         epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, bias,
-                       col_base + c * 32, gate_bf);
+                       col_base + c * 32, gate_bf, scr, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -497,7 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // are signalled in both CTAs by multicast commits; tmem_empty lives in the leader (16 epilogue warps arrive).
 constexpr int STAGES2 = 6;
 constexpr int STAGE2_BYTES = 2 * A_STAGE_BYTES;                 // per CTA: A 128x64 + W 128x64 (bf16)
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + 8 * 4096;      // + per-warp epilogue scratch
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -645,6 +669,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== epilogue (both CTAs, 128 rows each) =====================
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
+    float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)) + (warp - 4) * 4096);
     int it = 0;
     pdl_wait();
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
@@ -671,7 +696,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += 2)
         epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, p.bias,
-                       col_base + c * 32, gate_bf);
+                       col_base + c * 32, gate_bf, scr, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
@@ -779,10 +804,12 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
   return AT_OK;
 }
 int g_pair_mode = 1;      // 0: never use the CTA-pair kernel (developer switch, ARTALK_GEMM_PAIR=0)
+int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
 }  // namespace
 
 void set_gemm_pair_mode(int on) { g_pair_mode = on; }
+void set_gemm_force_bn(int bn) { g_force_bn = bn; }
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AT_OK;
@@ -863,6 +890,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     for (int i = 0; i < 4; ++i) {
       if (g.qkv_mode && cand[i] < 128) continue;                 // fused q/k/v epilogue needs whole heads per warp
       if (cand[i] > 32 && cand[i] / 2 >= g.N) continue;          // tile mostly padding
+      if (g_force_bn && cand[i] != g_force_bn && !(g.qkv_mode && g_force_bn < 128)) continue;
       const long tiles = m_tiles * ceil_div(g.N, cand[i]);
       const long waves = tiles / g_num_sms, rem = tiles % g_num_sms;
       double cost = (double)waves * tile_time[i];
