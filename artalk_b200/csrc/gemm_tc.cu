@@ -463,7 +463,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol, a);
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + 32, b2);
             const int col0 = col_base + hd * 64;
-            if (!row_ok || col0 >= p.N) continue;
+            if (col0 >= p.N) continue;                                   // warp-uniform
             if (bias) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -485,10 +485,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);                     // F.normalize eps
               if (is_q) scale *= p.head_scale[hc >> 6];
             }
-            bf16* dst;
-            if (is_q) dst = p.qbuf + (int64_t)r * p.qkv_C + hc;
-            else dst = (is_k ? p.kcache : p.vcache) + (int64_t)layer * p.kv_layer_stride + p.kv_map.off(r) + hc;
-            store_head_bf16(dst, a, b2, scale);
+            // the head's 32 rows x 128 B leave through the warp's scratch so that every store instruction covers 4 full lines
+            bf16* dst = is_q ? p.qbuf + hc : (is_k ? p.kcache : p.vcache) + (int64_t)layer * p.kv_layer_stride + hc;
+            const int64_t row_off = !row_ok ? 0 : (is_q ? (int64_t)r * p.qkv_C : p.kv_map.off(r));
+            uint4* scr4 = reinterpret_cast<uint4*>(scr);
+            const int sw = lane & 7;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const float* src = ch < 4 ? &a[ch * 8] : &b2[(ch - 4) * 8];
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(src[0] * scale, src[1] * scale), h1 = __floats2bfloat162_rn(src[2] * scale, src[3] * scale);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(src[4] * scale, src[5] * scale), h3 = __floats2bfloat162_rn(src[6] * scale, src[7] * scale);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              scr4[lane * 8 + (ch ^ sw)] = pk;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it2 = 0; it2 < 8; ++it2) {
+              const int j = it2 * 4 + (lane >> 3), ch = lane & 7;
+              const int64_t off_j = __shfl_sync(0xffffffffu, row_off, j);
+              const bool ok_j = __shfl_sync(0xffffffffu, (int)row_ok, j) != 0;
+              const uint4 val = scr4[j * 8 + (ch ^ (j & 7))];
+              if (ok_j) *reinterpret_cast<uint4*>(dst + off_j + ch * 8) = val;
+            }
+            __syncwarp();
           }
         }
       } else {
