@@ -179,8 +179,9 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
       for (int j = 0; j < 4; ++j) gpre[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gate) + g_off + col0) + j);
     }
     if (use_r && live) {
-      // row-per-thread 16-byte loads, in flight while the accumulator is read (a transposed, coalesced variant of this load
-      // measured 50 % slower: it has to land in shared memory before the tcgen05.ld, which serialises the two latencies)
+      // row-per-thread 16-byte loads, in flight while the accumulator is read. Two transposed, coalesced variants of this
+      // load (landing in the scratch before the tcgen05.ld; requested one chunk ahead into registers) measured 25-50 %
+      // slower on the residual GEMMs (out-proj 110 -> 140-180 us), unlike the stores, so the loads stay per thread
 #pragma unroll
       for (int j = 0; j < 8; ++j) rpre[j] = *(reinterpret_cast<const float4*>(p.resid + r_off + col0) + j);
     }
