@@ -238,7 +238,7 @@ def main():
     gemm_tflops = fl_g / (ms_g * 1e-3) / 1e12 if ms_g > 0 else 0.0
     top_tflops = fl_top * n_top / (ms_top * 1e-3) / 1e12 if ms_top > 0 else 0.0
     peak = tf_sus if args.precision == "bf16" else 72.0
-    # ncu --set full capture of the dominant launches (profiles/r1g_ncu_full_summary.md): dram read + write per launch;
+    # ncu --set full capture of the dominant launches (profiles/r1h_ncu_full_summary.md): dram read + write per launch;
     # only valid for the default workload's wav2vec FFN GEMMs (M = clips*chunks*199 = 38208, N x K = 4096 x 1024 / 1024 x 4096)
     is_default_top = args.precision == "bf16" and abs(fl_top - 2.0 * 38208 * 4096 * 1024) < 1.0
     roofline = {"bound": "tensor",
@@ -246,10 +246,10 @@ def main():
                            "step: %.1f GFLOP per launch, %d launches" % (fl_top / 1e9, int(n_top))) if args.precision == "bf16"
                 else "gemm_simt_kernel (fp32 CUDA-core GEMM)",
                 "achieved": top_tflops, "peak": peak, "unit": "TFLOP/s", "frac": top_tflops / peak,
-                "traffic": 492.0e6 if is_default_top else None,
+                "traffic": 506.2e6 if is_default_top else None,
                 "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the two wav2vec FFN GEMMs that "
-                                "share this flop count: FFN1 38208x4096x1024 86.9+259.9 MB (algorithmic 78 A + 8 W + 313 out), "
-                                "FFN2 38208x1024x4096 513.4+123.8 MB (algorithmic 313 A + 8 W + 157 resid read + 157 write)"
+                                "share this flop count: FFN1 38208x4096x1024 86.8+263.9 MB (algorithmic 78 A + 8 W + 313 out), "
+                                "FFN2 38208x1024x4096 533.2+128.5 MB (algorithmic 313 A + 8 W + 157 resid read + 157 write)"
                 if is_default_top else None,
                 "peak_source": ("%s bf16_tflops_sustained (kernel timed inside a long step)" % src) if args.precision == "bf16"
                 else "nominal fp32 FMA peak 148 SMs x 128 lanes x 2 x 1.9 GHz",
