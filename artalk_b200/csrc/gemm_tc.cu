@@ -32,6 +32,7 @@ struct TcParams {
   // tail split: the last (partial) wave's tiles [main_tiles, main_tiles + r) are cut into `tail_split` column slices of
   // `tail_bn` columns each, so the ragged wave costs tail_bn/BN of a full one (total_tiles counts the slices)
   int main_tiles, tail_split, tail_bn;
+  int tma_resid;           // pair kernel, EPI 1: the fp32 residual tile arrives by TMA (plain [M, N] residual, N % 32 == 0)
   int num_kb;              // K blocks of 64
   int tap_mode, tap_pad;   // tap mode: k-block j reads rows shifted by (j - tap_pad), columns of group g
   int a_group_cols;        // column offset per group in the A view (tap mode)
@@ -165,7 +166,9 @@ constexpr int EPI_SCRATCH_BYTES = 8 * 4096;       // 8 epilogue warps x (32 rows
 
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, bool row_ok, int64_t c_off, int64_t g_off, int64_t r_off,
-                                          const float* bias, int col0, bool gate_bf, float4* scr, int lane) {
+                                          const float* bias, int col0, bool gate_bf, float4* scr, int lane,
+                                          const float4* rsm = nullptr) {
+    // rsm: this thread's residual row of the chunk in shared memory (128 B, TMA 128-byte swizzle), or null
     const bool live = row_ok && col0 < p.N;
     const bool full = p.vec_ok && (col0 + 32 <= p.N);            // warp-uniform
     const int sw = lane & 7;
@@ -178,7 +181,10 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
 #pragma unroll
       for (int j = 0; j < 4; ++j) gpre[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gate) + g_off + col0) + j);
     }
-    if (use_r && live) {
+    if (use_r && rsm) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rpre[j] = rsm[j ^ sw];
+    } else if (use_r && live) {
       // row-per-thread 16-byte loads, in flight while the accumulator is read. Two transposed, coalesced variants of this
       // load (landing in the scratch before the tcgen05.ld; requested one chunk ahead into registers) measured 25-50 %
       // slower on the residual GEMMs (out-proj 110 -> 140-180 us), unlike the stores, so the loads stay per thread
@@ -241,7 +247,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
           v[j] *= gv[0]; v[j + 1] *= gv[1]; v[j + 2] *= gv[2]; v[j + 3] *= gv[3];
         }
       }
-      if (use_r && live) {
+      if (use_r && (live || rsm)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[j * 4] += rpre[j].x; v[j * 4 + 1] += rpre[j].y; v[j * 4 + 2] += rpre[j].z; v[j * 4 + 3] += rpre[j].w;
@@ -541,7 +547,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // the two shared memories, and each CTA gets its 128 accumulator rows in its own TMEM for the epilogue.
 // Barriers: full[s] lives in the leader (both producers arrive, both CTAs' TMA bytes complete on it); empty[s] / tmem_full
 // are signalled in both CTAs by multicast commits; tmem_empty lives in the leader (16 epilogue warps arrive).
-constexpr int STAGES2 = 6;
+constexpr int STAGES2 = 6;                                     // EPI 1 runs 5 stages: 32 KB become two residual-chunk buffers
+constexpr int RBUF_BYTES = 128 * 128;                          // 128 rows x 32 fp32
 constexpr int STAGE2_BYTES = 2 * A_STAGE_BYTES;                 // per CTA: A 128x64 + W 128x64 (bf16)
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + 8 * 4096;      // + per-warp epilogue scratch
 
@@ -591,11 +598,15 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                const __grid_constant__ CUtensorMap tmWt, const TcParams p) {
+                const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   constexpr int BN = 256;
+  constexpr int NST = EPI == 1 ? STAGES2 - 1 : STAGES2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
+  const uint32_t rbuf_base = smem_base + NST * STAGE2_BYTES;                       // EPI 1: 2 x RBUF_BYTES (1024-aligned)
+  const uint32_t bar_base = rbuf_base + (EPI == 1 ? 2 * RBUF_BYTES : 0);
+  auto rfull_bar = [&](int h) { return bar_base + 8u * (2 * STAGES2 + 5 + h); };
+  auto rempty_bar = [&](int h) { return bar_base + 8u * (2 * STAGES2 + 7 + h); };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + a); };
@@ -612,6 +623,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
+    for (int h = 0; h < 2; ++h) { mbar_init(rfull_bar(h), 1); mbar_init(rempty_bar(h), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -659,7 +671,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           else mbar_arrive_cluster(lead_full);
           tma_load_3d_2sm(sa, &tmA, lead_full, kb * BK, mt * 256 + (int)rank * 128, b);
           tma_load_3d_2sm(sb, bn == BN ? &tmW : &tmWt, lead_full, kb * BK, col_base + (int)rank * w_rows, 0);
-          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -682,9 +694,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int k = 0; k < BK / UMMA_K; ++k)
             tc_mma_bf16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit_2sm(empty_bar(stage));         // frees the slot in both CTAs once these MMAs have read it
-          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
         tc_commit_2sm(tfull_bar(acc));             // accumulator ready for both CTAs' epilogues
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== residual producer (EPI 1, both CTAs): one 128-row x 32-column fp32 chunk per TMA =====================
+    // Chunks are requested in the order the two epilogue halves consume them (half h owns chunks h, h+2, ... and buffer h), so
+    // a chunk lands while the previous one of that half is processed: no global-load latency on the epilogue's critical path.
+    if (EPI == 1 && p.tma_resid && lane == 0) {
+      uint32_t use[2] = {0u, 0u};
+      pdl_wait();
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+        int col_base, bn, mt, b;
+        decode(tile, col_base, bn, mt, b);
+        const int row0 = b * p.rpb + mt * 256 + (int)rank * 128;
+        for (int c = 0; c < (bn >> 5); ++c) {
+          const int h = c & 1;
+          mbar_wait(rempty_bar(h), (use[h] & 1u) ^ 1u, p.err_flag, 0x25);
+          mbar_arrive_expect_tx(rfull_bar(h), (uint32_t)RBUF_BYTES);
+          tma_load_3d(rbuf_base + h * RBUF_BYTES, &tmR, rfull_bar(h), col_base + c * 32, row0, 0);
+          ++use[h];
+        }
       }
     }
   } else if (warp >= 4) {
@@ -693,6 +725,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
     float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)) + (warp - 4) * 4096);
     int it = 0;
+    uint32_t r_use = 0;
     pdl_wait();
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
       int col_base, bn, mt, b;
@@ -710,15 +743,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int col0 = col_base + c * 32;
           if (col0 + 32 > p.N) break;
           if (gate_bf) prefetch_l2(reinterpret_cast<const bf16*>(p.gate) + g_off + col0);
-          if (p.resid) prefetch_l2(p.resid + r_off + col0);
+          if (p.resid && !p.tma_resid) prefetch_l2(p.resid + r_off + col0);
         }
       }
       mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 0x24);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = half; c < n_chunks; c += 2)
+      for (int c = half; c < n_chunks; c += 2) {
+        const float4* rsm = nullptr;
+        if (EPI == 1 && p.tma_resid) {
+          mbar_wait(rfull_bar(half), r_use & 1u, p.err_flag, 0x26);
+          rsm = reinterpret_cast<const float4*>(smem_raw + (rbuf_base - smem_u32(smem_raw)) + half * RBUF_BYTES + (q * 32 + lane) * 128);
+        }
         epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, p.bias,
-                       col_base + c * 32, gate_bf, scr, lane);
+                       col_base + c * 32, gate_bf, scr, lane, rsm);
+        if (EPI == 1 && p.tma_resid) {             // the row was copied to registers at the top of epi_chunk
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rempty_bar(half));
+          ++r_use;
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
@@ -751,14 +795,14 @@ EncodeTiledFn get_encode() {
 }
 
 int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes,
-                uint32_t b0, uint32_t b1) {
+                uint32_t b0, uint32_t b1, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   EncodeTiledFn enc = get_encode();
   AT_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {s1_bytes, s2_bytes};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, dtype, 3, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -798,7 +842,8 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
 }
 
 template <int EPI>
-int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const TcParams& p, cudaStream_t st) {
+int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmR, const TcParams& p,
+                    cudaStream_t st) {
   static int max_clusters = -1;
   if (max_clusters < 0) {
     AT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -821,17 +866,19 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_on() ? 2 : 1;
-  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, tmWt, p));
+  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, tmWt, tmR, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
 int g_pair_mode = 1;      // 0: never use the CTA-pair kernel (developer switch, ARTALK_GEMM_PAIR=0)
+int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
 }  // namespace
 
 void set_gemm_pair_mode(int on) { g_pair_mode = on; }
 void set_gemm_force_bn(int bn) { g_force_bn = bn; }
+void set_gemm_tma_resid(int on) { g_tma_resid = on; }
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AT_OK;
@@ -850,6 +897,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     AT_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   TcParams p;
+  p.tma_resid = 0;
   p.N = g.N;
   const bool batched = g.a_map.rpb > 0;
   p.rpb = batched ? g.a_map.rpb : g.M;
@@ -894,8 +942,15 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
       if (p.tail_split > 1)
         AT_TRY(make_map_3d(&tmW2t, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.ldw * 2, (uint64_t)g.N * g.ldw * 2, BK,
                            (uint32_t)(p.tail_bn / 2)));
-      if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, tmW2t, p, st);
-      return launch_pair_epi<0>(tmA2, tmW2, tmW2t, p, st);
+      // fp32 residual by TMA: plain contiguous-row residual, 16-byte aligned rows, whole 32-column chunks
+      CUtensorMap tmR = tmW2;
+      p.tma_resid = (g_tma_resid && g.resid && !g.gate && p.vec_ok && g.resid_map.rpb <= 0 && g.N % 32 == 0 && g.resid_map.rs % 4 == 0 &&
+                     ((uintptr_t)g.resid % 16 == 0)) ? 1 : 0;
+      if (p.tma_resid)
+        AT_TRY(make_map_3d(&tmR, g.resid, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.resid_map.rs * 4, (uint64_t)g.M * g.resid_map.rs * 4,
+                           32, 128, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
+      if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, tmW2t, tmR, p, st);
+      return launch_pair_epi<0>(tmA2, tmW2, tmW2t, tmR, p, st);
     }
   }
   // N-tile choice: persistent CTAs on 148 SMs quantise badly for the recurrence's GEMMs (e.g. 50 x 3 tiles of 128x256 =

@@ -70,6 +70,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 // developer switch: 0 = never use the CTA-pair (cta_group::2) kernel for large GEMMs
 void set_gemm_pair_mode(int on);
 void set_gemm_force_bn(int bn);
+void set_gemm_tma_resid(int on);
 
 // ---------------- attention.cu ----------------
 struct AttnArgs {

@@ -65,10 +65,12 @@ def test_gemm_bias_act(pname, prec, dt, tol, M, N, K, act):
     assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("M,N,K,act,resid", [(9472, 2048, 256, 1, False), (9700, 2048, 512, 0, True), (18944, 1280, 192, 2, True), (9728, 2048, 128, 0, False)])
-def test_gemm_cta_pair_kernel(M, N, K, act, resid):
+@pytest.mark.parametrize("M,N,K,act,resid,gated", [(9472, 2048, 256, 1, False, False), (9700, 2048, 512, 0, True, True),
+                                                   (18944, 1280, 192, 2, True, True), (9728, 2048, 128, 0, False, False),
+                                                   (9700, 2048, 512, 0, True, False), (18944, 1280, 192, 3, True, False)])
+def test_gemm_cta_pair_kernel(M, N, K, act, resid, gated):
     """Large plain GEMMs take the cta_group::2 kernel (256x256 tiles over two SMs): same results as the fp64 reference,
-    including a ragged last M tile, a ragged N tile (1280 = 5 x 256), a ragged last wave (304 tiles on 74 CTA pairs: the last 8
+    including a ragged last M tile, a ragged N tile (1280 = 5 x 256), the TMA-fed residual tile (residual without gate), a ragged last wave (304 tiles on 74 CTA pairs: the last 8
     tiles run as 32-column slices), gate + in-place residual and dual outputs."""
     dt, tol = torch.bfloat16, 3e-2
     g = torch.Generator(device="cpu").manual_seed(M + N)
@@ -77,11 +79,12 @@ def test_gemm_cta_pair_kernel(M, N, K, act, resid):
     b = torch.randn(N, generator=g).to(dev())
     if resid:
         x = torch.randn(M, N, generator=g).to(dev())
-        gate = torch.randn(M, N, generator=g).to(dev(), dt)
+        gate = torch.randn(M, N, generator=g).to(dev(), dt) if gated else None
         x0 = x.clone()
         xa = torch.empty(M, N, device=dev(), dtype=dt)
         run_gemm(1, A, W, M, N, K, bias=b, act=act, gate=gate, resid=x, out32=x, out_act=xa)
-        ref = (x0.double() + ACTS[act](A.double() @ W.double().t() + b.double()) * gate.double()).float()
+        ref = ACTS[act](A.double() @ W.double().t() + b.double())
+        ref = (x0.double() + (ref * gate.double() if gated else ref)).float()
         scale = max(1.0, ref.abs().max().item())
         assert (x - ref).abs().max().item() < tol * scale
         assert (xa.float() - ref).abs().max().item() < (tol + 8e-3) * scale
