@@ -83,7 +83,24 @@ __global__ void __launch_bounds__(256) bits_tokens_kernel(BitsTables tb, const u
     __syncthreads();
     if (n < C) {
       const int row0 = tb.cum[q - 1];
-      for (int r = 0; r < pq; ++r) {
+      // 4 rows per iteration with their position-embedding loads issued up front: one dependent L2 round trip per row made
+      // this loop (up to 100 rows) the whole cost of the kernel
+      int r = 0;
+      for (; r + 4 <= pq; r += 4) {
+        float pv[4], a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pv[u] = __ldg(pos + (int64_t)(row0 + r + u) * C + n);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[u] = be;
+#pragma unroll
+          for (int c = 0; c < CD; ++c) a[u] = fmaf(feat[r + u][c], w[c], a[u]);
+          a[u] += pv[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) oc[(int64_t)(row0 - base_row + r + u) * C + n] = from_f32<TO>(a[u]);
+      }
+      for (; r < pq; ++r) {
         float a = be;
 #pragma unroll
         for (int c = 0; c < CD; ++c) a = fmaf(feat[r][c], w[c], a);
