@@ -137,6 +137,14 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"gemm_force_bn", int(os.environ["ARTALK_GEMM_FORCE_BN"]))
         if os.environ.get("ARTALK_ATTN_SIMT_MAX_LQ"):
             l.artalk_set_option(b"attn_simt_max_lq", int(os.environ["ARTALK_ATTN_SIMT_MAX_LQ"]))
+        if os.environ.get("ARTALK_SKINNY_MAX_M"):         # 0: the latency-path kernels (skinny.cu) are never taken
+            l.artalk_set_option(b"skinny_max_m", int(os.environ["ARTALK_SKINNY_MAX_M"]))
+        if os.environ.get("ARTALK_AR_SMALL"):             # 0: the few-token scale steps run as separate kernels
+            l.artalk_set_option(b"ar_small", int(os.environ["ARTALK_AR_SMALL"]))
+        if os.environ.get("ARTALK_SKINNY_TOKENS"):
+            l.artalk_set_option(b"skinny_tokens", int(os.environ["ARTALK_SKINNY_TOKENS"]))
+        if os.environ.get("ARTALK_ATTN_FEW_MAX_LQ"):
+            l.artalk_set_option(b"attn_few_max_lq", int(os.environ["ARTALK_ATTN_FEW_MAX_LQ"]))
         if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":
             l.artalk_set_option(b"gemm_pair", 0)
         _lib = l

@@ -32,6 +32,8 @@ int artalk_destroy(artalk_engine_t* e) {
   if (!e) return AT_OK;
   e->eng.drop_graphs();
   if (e->eng.ws) cudaFree(e->eng.ws);
+  if (e->eng.ar_table) cudaFree(e->eng.ar_table);
+  if (e->eng.ar_sync) cudaFree(e->eng.ar_sync);
   delete e;
   return AT_OK;
 }
@@ -154,6 +156,10 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "gemm_force_bn")) { set_gemm_force_bn(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_tma_resid")) { set_gemm_tma_resid(value); return AT_OK; }
   if (!std::strcmp(name, "attn_simt_max_lq")) { set_attn_simt_max_lq(value); return AT_OK; }
+  if (!std::strcmp(name, "ar_small")) { set_ar_small(value); return AT_OK; }
+  if (!std::strcmp(name, "skinny_tokens")) { g_skinny_tokens = value; return AT_OK; }
+  if (!std::strcmp(name, "skinny_max_m")) { set_skinny_max_m(value); return AT_OK; }
+  if (!std::strcmp(name, "attn_few_max_lq")) { set_attn_few_max_lq(value); return AT_OK; }
   set_last_error("artalk_set_option: unknown option '%s'", name);
   return AT_EINVAL;
 }
@@ -177,6 +183,7 @@ int artalk_op_gemm(const artalk_gemm_t* a, int precision, void* stream) {
   g.bias = a->bias; g.act = a->act; g.gate = a->gate; g.gate_dt = a->gate_dt; g.gate_map = rm(a->gate_map);
   g.resid = a->resid; g.resid_map = rm(a->resid_map); g.out32 = a->out32; g.out_act = a->out_act; g.out_act_dt = a->out_act_dt;
   g.c_map = rm(a->c_map);
+  g.skinny = 1;                 // op-level calls: any shape within option "skinny_max_m" may take the latency kernel
   return precision == ARTALK_PRECISION_FP32 ? launch_gemm_simt(g, (cudaStream_t)stream) : launch_gemm_tc(g, (cudaStream_t)stream);
 }
 

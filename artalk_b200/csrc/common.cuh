@@ -62,8 +62,8 @@ struct RowMap {
     return (int64_t)b * bs + (int64_t)(r - b * rpb) * rs;
   }
 };
-static inline RowMap plain_rows(int64_t rs) { RowMap m; m.rpb = 0; m.bs = 0; m.rs = rs; return m; }
-static inline RowMap batched_rows(int rpb, int64_t bs, int64_t rs) { RowMap m; m.rpb = rpb; m.bs = bs; m.rs = rs; return m; }
+__host__ __device__ static inline RowMap plain_rows(int64_t rs) { RowMap m; m.rpb = 0; m.bs = 0; m.rs = rs; return m; }
+__host__ __device__ static inline RowMap batched_rows(int rpb, int64_t bs, int64_t rs) { RowMap m; m.rpb = rpb; m.bs = bs; m.rs = rs; return m; }
 
 enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_LEAKY02 = 3, ACT_SILU = 4 };
 
@@ -172,6 +172,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 extern bool g_pdl;        // host switch (artalk_enable_pdl); default on
 extern int g_pdl_w2v_max_chunks;   // wav2vec sub-batches larger than this run without PDL (option "pdl_w2v_max_chunks")
+extern int g_skinny_tokens;   // option "skinny_tokens" (engine.cu)
 extern int g_pdl_mask;    // per kernel class (option "pdl_mask"): 1 = tcgen05 GEMM, 2 = tcgen05 attention, 4 = everything else
 #ifndef ARTALK_PDL_CLASS
 #define ARTALK_PDL_CLASS 4

@@ -148,6 +148,17 @@ int Engine::finalize() {
   for (int i = 0; i < c.n_levels; ++i) { tb.pn[i] = c.patch_nums[i]; cum += c.patch_nums[i]; tb.cum[i] = cum; }
   tb.up_i0 = get<int>("tb.up_i0"); tb.up_i1 = get<int>("tb.up_i1"); tb.up_w1 = get<float>("tb.up_w1");
   tb.pool_start = get<int>("tb.pool_start"); tb.pool_end = get<int>("tb.pool_end");
+  if (c.precision == 1 && !ar_table) {
+    std::vector<char> host(ar_layer_table_bytes(c.ar_depth));
+    for (int l = 0; l < c.ar_depth; ++l)
+      ar_layer_table_fill(host.data(), l, getw(S("ar.l%d.qkv.w", l)), getw(S("ar.l%d.proj.w", l)), getw(S("ar.l%d.ff1.w", l)),
+                          getw(S("ar.l%d.ff2.w", l)), get<float>(S("ar.l%d.qkv.b", l)), get<float>(S("ar.l%d.proj.b", l)),
+                          get<float>(S("ar.l%d.ff1.b", l)), get<float>(S("ar.l%d.ff2.b", l)), get<float>(S("ar.l%d.head_scale", l)));
+    AT_CUDA(cudaMalloc(&ar_table, host.size()));
+    AT_CUDA(cudaMemcpy(ar_table, host.data(), host.size(), cudaMemcpyHostToDevice));
+    AT_CUDA(cudaMalloc((void**)&ar_sync, 2 * sizeof(unsigned int)));
+    AT_CUDA(cudaMemset(ar_sync, 0, 2 * sizeof(unsigned int)));
+  }
   finalized = true;
   return AT_OK;
 }
@@ -180,6 +191,7 @@ void* Engine::ws_alloc(size_t bytes) {
 
 unsigned long long g_launch_count = 0;
 bool g_pdl = true;
+int g_skinny_tokens = 1;        // AR scale steps with at most this many new tokens per clip take the latency kernels (option "skinny_tokens")
 int g_pdl_mask = 3;            // measured in the chunk graph: GEMM/attention edges help (-3.4 %), elementwise edges cancel it
 int g_pdl_w2v_max_chunks = 1 << 30;
 
@@ -723,11 +735,27 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
   }
   for (int p = 0; p < c.n_levels; ++p) {
     const int n_new = c.patch_nums[p], off = p ? tb.cum[p - 1] : 0, M = B * n_new;
+    const int sk = n_new <= g_skinny_tokens ? 1 : 0;           // per-clip criterion: batch-size independent arithmetic
     const RowMap ada_map = batched_rows(n_new, (int64_t)L * n_ada, n_ada);
     const char* ada_p = ada + (size_t)off * n_ada * s;
     const uint32_t* src_words = forced_words ? forced_words : words;
     AT_TRY(launch_bits_tokens(tb, src_words, L, style, get<float>("ar.embed.w"), get<float>("ar.embed.b"), get<float>("ar.lvl_pos"), x,
                               DT_F32, B, p, p, C, st));
+    if (defer && ar_table && ar_small_supported(B, n_new, C, P + off + n_new, 2 * c.code_dim)) {
+      // few new tokens per clip: every block + the head in one launch (skinny.cu)
+      ArSmallArgs sa;
+      sa.B = B; sa.n_new = n_new; sa.C = C; sa.NL = NL; sa.lk = P + off + n_new; sa.n_logits = 2 * c.code_dim;
+      sa.x = x; sa.y = ybuf; sa.u = u; sa.qbuf = qbuf; sa.o = o; sa.f = f;
+      sa.ada = ada_p; sa.ada_map = ada_map;
+      sa.kcache = kcache; sa.vcache = vcache; sa.kv_layer_stride = (int64_t)B * KV * C; sa.kv_seq_stride = (int64_t)KV * C;
+      sa.kv_new_off = (int64_t)(P + off) * C; sa.kv_new_map = batched_rows(n_new, (int64_t)KV * C, C);
+      sa.layer_table = ar_table; sa.whead = getw("ar.head.w"); sa.bhead = get<float>("ar.head.b");
+      sa.logits = logits + (size_t)off * 2 * c.code_dim; sa.logits_map = batched_rows(n_new, (int64_t)L * 2 * c.code_dim, 2 * c.code_dim);
+      sa.sync = ar_sync; sa.eps = 1e-6f;
+      AT_TRY(launch_ar_small(sa, st));
+      AT_TRY(launch_argmax_bits(logits + (size_t)off * 2 * c.code_dim, sa.logits_map, words + off, batched_rows(n_new, L, 1), M, st));
+      continue;
+    }
     bool pending = false;                                    // ybuf holds the previous layer's FFN2 output, gate gamma2 of that layer
     for (int l = 0; l < NL; ++l) {
       const char* ada_l = ada_p + (size_t)l * 6 * C * s;     // chunk order: g1, g2, s1, s2, b1, b2 (quirk 9)
@@ -735,7 +763,7 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
       pending = false;
       g = gemm_args();
       g.A = u; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.qkv.w", l)); g.ldw = C; g.M = M; g.N = 3 * C; g.K = C;
-      g.bias = get<float>(S("ar.l%d.qkv.b", l));
+      g.bias = get<float>(S("ar.l%d.qkv.b", l)); g.skinny = sk;
       char* kc = kcache + (size_t)l * B * KV * C * s; char* vc = vcache + (size_t)l * B * KV * C * s;
       if (fused_qkv) {
         g.qkv_mode = 1; g.qkv_C = C; g.head_scale = get<float>(S("ar.l%d.head_scale", l)); g.qbuf = qbuf;
@@ -756,7 +784,7 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
       AT_TRY(attention(a, st));
       g = gemm_args();
       g.A = o; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.proj.w", l)); g.ldw = C; g.M = M; g.N = C; g.K = C;
-      g.bias = get<float>(S("ar.l%d.proj.b", l)); g.c_map = plain_rows(C);
+      g.bias = get<float>(S("ar.l%d.proj.b", l)); g.c_map = plain_rows(C); g.skinny = sk;
       if (defer) g.out32 = ybuf;
       else { g.gate = ada_l; g.gate_dt = adt; g.gate_map = ada_map; g.resid = x; g.resid_map = plain_rows(C); g.out32 = x; }   // gamma1
       AT_TRY(gemm(g, st));
@@ -764,10 +792,11 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
       g = gemm_args();
       g.A = u; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.ff1.w", l)); g.ldw = C; g.M = M; g.N = 4 * C; g.K = C;
       g.bias = get<float>(S("ar.l%d.ff1.b", l)); g.act = ACT_GELU_TANH; g.out_act = f; g.out_act_dt = adt; g.c_map = plain_rows(4 * C);
+      g.skinny = sk;
       AT_TRY(gemm(g, st));
       g = gemm_args();
       g.A = f; g.a_map = plain_rows(4 * C); g.W = getw(S("ar.l%d.ff2.w", l)); g.ldw = 4 * C; g.M = M; g.N = C; g.K = 4 * C;
-      g.bias = get<float>(S("ar.l%d.ff2.b", l)); g.c_map = plain_rows(C);
+      g.bias = get<float>(S("ar.l%d.ff2.b", l)); g.c_map = plain_rows(C); g.skinny = sk;
       if (defer) { g.out32 = ybuf; pending = true; }
       else { g.gate = ada_l + (size_t)C * s; g.gate_dt = adt; g.gate_map = ada_map; g.resid = x; g.resid_map = plain_rows(C); g.out32 = x; }   // gamma2
       AT_TRY(gemm(g, st));
@@ -778,7 +807,7 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
     g = gemm_args();
     g.A = u; g.a_map = plain_rows(C); g.W = getw("ar.head.w"); g.ldw = C; g.M = M; g.N = 2 * c.code_dim; g.K = C;
     g.bias = get<float>("ar.head.b"); g.out32 = logits + (size_t)off * 2 * c.code_dim;
-    g.c_map = batched_rows(n_new, (int64_t)L * 2 * c.code_dim, 2 * c.code_dim);
+    g.c_map = batched_rows(n_new, (int64_t)L * 2 * c.code_dim, 2 * c.code_dim); g.skinny = sk;
     AT_TRY(gemm(g, st));
     AT_TRY(launch_argmax_bits(logits + (size_t)off * 2 * c.code_dim, g.c_map, words + off, batched_rows(n_new, L, 1), M, st));
   }

@@ -71,6 +71,8 @@ struct Engine {
   std::map<int, GraphEntry> graphs;
   bool use_graphs = true;
   cudaStream_t gstream = nullptr; cudaEvent_t gev_in = nullptr, gev_out = nullptr;
+  // whole-stack kernel of the few-token scale steps (skinny.cu): per-block weight pointer table + barrier words (device)
+  void* ar_table = nullptr; unsigned int* ar_sync = nullptr;
   void drop_graphs() {
     for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     graphs.clear();

@@ -889,6 +889,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   AT_REQUIRE(((uintptr_t)g.A) % 16 == 0 && ((uintptr_t)g.W) % 16 == 0, "gemm_tc: operands must be 16-byte aligned");
   AT_REQUIRE(g.tap_w == 0 || (g.tap_w == BK && g.a_map.rpb > 0 && g.K % BK == 0), "gemm_tc: tap mode needs tap_w == 64");
   AT_REQUIRE(g.groups == 1 || g.tap_w > 0, "gemm_tc: groups are only supported in tap mode");
+  if (g.skinny && gemm_skinny_supported(g)) return launch_gemm_skinny(g, st);      // latency-bound shapes (few rows): skinny.cu
   if (!g_err_flag) {
     AT_CUDA(cudaMalloc((void**)&g_err_flag, sizeof(unsigned int)));
     AT_CUDA(cudaMemset(g_err_flag, 0, sizeof(unsigned int)));

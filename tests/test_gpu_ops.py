@@ -96,6 +96,58 @@ def test_gemm_cta_pair_kernel(M, N, K, act, resid, gated):
         assert (out.float() - ref).abs().max().item() < (tol + 8e-3) * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K,act,mode", [(64, 768, 3072, 0, "f32"), (64, 3072, 768, 2, "bf16"), (320, 768, 3072, 0, "f32"),
+                                             (320, 3072, 768, 2, "bf16"), (1, 768, 768, 0, "f32"), (5, 64, 768, 0, "rows"),
+                                             (100, 2304, 768, 1, "dual"), (200, 512, 512, 3, "resid"), (257, 1536, 512, 0, "bf16"),
+                                             (512, 768, 768, 4, "resid"), (1280, 2304, 768, 0, "bf16")])
+def test_gemm_skinny_latency_path(M, N, K, act, mode):
+    """GEMMs with few rows (the 1- and 5-token scale steps, every batch-1 step) take the mma.sync / cp.async kernel of
+    skinny.cu: same results as the fp64 reference and as the tcgen05 kernel (option skinny_max_m = 0) on ragged row slabs,
+    every column-tile width (8..64), deep and shallow rings, fp32 / bf16 / dual outputs, residual and batched output rows."""
+    dt, tol = torch.bfloat16, 3e-2
+    g = torch.Generator(device="cpu").manual_seed(M * 11 + N)
+    A = torch.randn(M, K, generator=g).to(dev(), dt)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev(), dt)
+    b = torch.randn(N, generator=g).to(dev())
+    ref = ACTS[act](A.double() @ W.double().t() + b.double()).float()
+    outs = []
+    for max_m in (2048, 0):
+        _lib.check(_lib.lib().artalk_set_option(b"skinny_max_m", max_m))
+        try:
+            if mode == "resid":
+                x = torch.randn(M, N, generator=torch.Generator(device="cpu").manual_seed(3)).to(dev())
+                want = x + ref
+                run_gemm(1, A, W, M, N, K, bias=b, act=act, resid=x, out32=x)
+                got = x
+            elif mode == "rows":          # logits rows scattered as (clip, token) like the AR head
+                buf = torch.full((M, 7, N), float("nan"), device=dev())
+                run_gemm(1, A, W, M, N, K, bias=b, act=act, out32=buf.view(-1)[2 * N:], c_map=rowmap(1, 7 * N, N))
+                assert torch.isnan(buf[:, :2]).all() and torch.isnan(buf[:, 3:]).all()
+                got, want = buf[:, 2], ref
+            elif mode == "dual":
+                got = torch.full((M, N), float("nan"), device=dev())
+                xa = torch.empty(M, N, device=dev(), dtype=dt)
+                run_gemm(1, A, W, M, N, K, bias=b, act=act, out32=got, out_act=xa)
+                assert (xa.float() - got).abs().max().item() <= 8e-3 * max(1.0, got.abs().max().item())
+                want = ref
+            elif mode == "bf16":
+                o = torch.full((M, N), float("nan"), device=dev(), dtype=dt)
+                run_gemm(1, A, W, M, N, K, bias=b, act=act, out_act=o)
+                got, want = o.float(), ref
+            else:
+                got = torch.full((M, N), float("nan"), device=dev())
+                run_gemm(1, A, W, M, N, K, bias=b, act=act, out32=got)
+                want = ref
+        finally:
+            _lib.check(_lib.lib().artalk_set_option(b"skinny_max_m", 2048))
+        assert torch.isfinite(got).all()
+        extra = 8e-3 if mode == "bf16" else 0.0
+        assert (got - want).abs().max().item() < (tol + extra) * max(1.0, want.abs().max().item())
+        outs.append(got.clone())
+    # the two kernels accumulate the same bf16 products in fp32: they agree far inside the bf16-vs-fp64 tolerance
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("pname,prec,dt,tol", precisions())
 def test_gemm_gate_residual_rowmaps(pname, prec, dt, tol):
     """AR epilogue: x += (A W^T + b) * gamma with gamma rows gathered through (clip, token) maps; dual outputs."""
@@ -171,7 +223,8 @@ def run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, scale, split=0):
 
 @pytest.mark.parametrize("dt,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("n_seq,H,D,lq,lk,split", [(3, 16, 64, 199, 199, 0), (2, 8, 64, 200, 200, 100), (4, 12, 64, 25, 212, 0),
-                                                   (5, 12, 64, 1, 182, 0), (2, 4, 32, 50, 50, 0), (2, 12, 64, 100, 362, 0)])
+                                                   (5, 12, 64, 1, 182, 0), (2, 4, 32, 50, 50, 0), (2, 12, 64, 100, 362, 0),
+                                                   (7, 12, 64, 5, 187, 0), (3, 12, 64, 8, 384, 0), (2, 8, 64, 3, 17, 0)])
 def test_attention(dt, tol, n_seq, H, D, lq, lk, split):
     g = torch.Generator(device="cpu").manual_seed(lq * 3 + lk)
     Cw = H * D
@@ -180,7 +233,19 @@ def test_attention(dt, tol, n_seq, H, D, lq, lk, split):
     v = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), dt)
     out = torch.empty(n_seq, lq, Cw, device=dev(), dtype=dt)
     scale = 0.3
-    run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), scale, split)
+    few = dt == torch.bfloat16 and lq <= 8 and D == 64          # also through the opt-in few-query kernel (skinny.cu)
+    for few_on in ((8, 0) if few else (0,)):
+        _lib.check(_lib.lib().artalk_set_option(b"attn_few_max_lq", few_on))
+        try:
+            out.fill_(float("nan"))
+            run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), scale, split)
+        finally:
+            _lib.check(_lib.lib().artalk_set_option(b"attn_few_max_lq", 0))
+        _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol)
+
+
+def _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol):
+    Cw = H * D
     qq = q.float().view(n_seq, lq, H, D).transpose(1, 2)
     kk = k.float().view(n_seq, lk, H, D).transpose(1, 2)
     vv = v.float().view(n_seq, lk, H, D).transpose(1, 2)

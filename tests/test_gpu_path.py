@@ -167,6 +167,42 @@ def test_inference_bf16_free_running(name):
     assert np.median(e0) < MOTION_TOL["bf16"], np.median(e0)        # first chunk: only isolated bit flips
 
 
+def test_whole_stack_kernel_matches_separate_kernels():
+    """Opt-in (option ar_small = 1): the few-token scale steps (1 and 5 new tokens per clip) run every AR block + the head
+    in ONE cooperative launch (skinny.cu::ar_small_kernel, grid-wide barriers between phases). Teacher-forced with the same bits, its logits agree with
+    the separate-kernel path (option ar_small = 0) at the bf16 rounding level, for a batch that spans several 64-row slabs
+    and in both graph-replayed and eager launches."""
+    from artalk_b200 import _lib
+    case = CASES["tiny_style"]
+    g = gu.load("tiny_style")
+    m = model("TINY", "bf16")
+    gold_words = torch.from_numpy(g["bits"].view(np.int32).copy())
+    gold_prev = torch.from_numpy(g["prev_bits"].view(np.int32).copy())
+    reps = 40                                                    # 80 clips: 80 / 400 rows in the two few-token steps
+    batch = {"audio": case.audio().repeat(reps, 1), "style_motion": case.style().repeat(reps, 1, 1)}
+    tw, tp = gold_words.repeat(reps, 1, 1), gold_prev.repeat(reps, 1, 1)
+    res = {}
+    for on in (1, 0):
+        _lib.check(_lib.lib().artalk_set_option(b"ar_small", on))
+        try:
+            for it in range(3):                                  # eager warm-up, capture, replay
+                tr = {}
+                out = m.inference(batch, trace=tr, teacher_words=tw, teacher_prev_words=tp)
+        finally:
+            _lib.check(_lib.lib().artalk_set_option(b"ar_small", 0))       # the default
+        res[on] = (tr["logits"].float().cpu(), out.cpu())
+    la, lb = res[1][0], res[0][0]
+    L = la.shape[-2]
+    few = la[..., :6, :] - lb[..., :6, :]                        # tokens of the 1- and 5-token scales
+    assert few.abs().max().item() < 0.25 and few.abs().mean().item() < 0.02, (few.abs().max().item(), few.abs().mean().item())
+    rest = la[..., 6:, :] - lb[..., 6:, :]                       # later scales see the keys / values the kernel cached
+    assert rest.abs().max().item() < 0.25 and rest.abs().mean().item() < 0.02
+    err = np.abs(la[:2].numpy() - g["logits"])
+    assert err.max() < 0.6 and err.mean() < 0.04
+    assert torch.equal(la[:2], la[2:4]) and torch.equal(res[1][1][:2], res[1][1][-2:])       # identical clips -> identical rows
+    assert (res[1][1] - res[0][1]).abs().max().item() < MOTION_TOL["bf16"]
+
+
 # ----------------------------------------------------------------------------- properties
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_batched_equals_per_clip_loop(precision):
