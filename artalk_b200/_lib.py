@@ -84,6 +84,7 @@ SYMBOLS = {
     "artalk_set_workspace_limit": (C.c_int, [C.c_void_p, C.c_size_t]),
     "artalk_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "artalk_enable_graphs": (C.c_int, [C.c_void_p, C.c_int]),
+    "artalk_set_latency_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "artalk_audio_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "artalk_style_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "artalk_motion_to_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -59,6 +59,13 @@ int artalk_enable_graphs(artalk_engine_t* e, int enable) {
   return AT_OK;
 }
 
+int artalk_set_latency_mode(artalk_engine_t* e, int max_rows) {
+  AT_REQUIRE(e && max_rows >= 0, "artalk_set_latency_mode: bad argument");
+  if (e->eng.latency_rows != max_rows) e->eng.drop_graphs();
+  e->eng.latency_rows = max_rows;
+  return AT_OK;
+}
+
 int artalk_audio_encode(artalk_engine_t* e, const float* audio, int n_chunks, float* cond, void* stream) {
   AT_REQUIRE(e && audio && cond && n_chunks >= 0, "artalk_audio_encode: bad argument");
   return e->eng.audio_encode(audio, n_chunks, cond, (cudaStream_t)stream);

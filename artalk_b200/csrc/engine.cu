@@ -281,7 +281,10 @@ int Engine::prof_read(double* out, cudaStream_t st) {
     return AT_OK;                                                               \
   } while (0)
 
-int Engine::gemm(const GemmArgs& g, cudaStream_t st) {
+int Engine::gemm(const GemmArgs& g0, cudaStream_t st) {
+  GemmArgs g = g0;
+  // latency mode: few rows and a small output (the hoisted AdaLN / previous-chunk K/V GEMMs stay on the tensor-core kernel)
+  if (latency_rows > 0 && g.M <= latency_rows && (int64_t)g.M * g.N <= ((int64_t)1 << 21)) g.skinny = 1;
   PROF_WRAP(0, 2.0 * g.M * g.N * g.K * g.groups, cfg.precision == 0 ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st));
 }
 

@@ -73,6 +73,7 @@ struct Engine {
   cudaStream_t gstream = nullptr; cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   // whole-stack kernel of the few-token scale steps (skinny.cu): per-block weight pointer table + barrier words (device)
   void* ar_table = nullptr; unsigned int* ar_sync = nullptr;
+  int latency_rows = 0;      // artalk_set_latency_mode: GEMMs with at most this many rows take the latency kernel (0 = off)
   void drop_graphs() {
     for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     graphs.clear();

@@ -103,9 +103,10 @@ __device__ __forceinline__ void sk_tile(const SkParams& p, const int col0, const
   const bf16* a_src[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    int gr = row0 + r_lo + 16 * j;
-    gr = gr < p.M ? gr : p.M - 1;                       // rows past M are computed on a valid row and never stored
-    a_src[j] = p.A + p.a_map.off(gr) + pc * 8;
+    // rows past M are not loaded (their accumulators see whatever the ring holds and are never stored). Clamping them to
+    // a valid row instead made every CTA hammer the same few cache lines: 63 us for M = 1, K = 3072
+    const int gr = row0 + r_lo + 16 * j;
+    a_src[j] = gr < p.M ? p.A + p.a_map.off(gr) + pc * 8 : nullptr;
   }
   auto load_w = [&](int chunk, int slot) {
     const uint32_t dst = sbase + slot * STAGE + SK_A_STAGE + pc * 16;
@@ -118,7 +119,8 @@ __device__ __forceinline__ void sk_tile(const SkParams& p, const int col0, const
   auto load_a = [&](int chunk, int slot) {
     const uint32_t dst = sbase + slot * STAGE + pc * 16;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cp_async16(dst + (r_lo + 16 * j) * SK_PITCH, a_src[j] + chunk * SK_KC);
+    for (int j = 0; j < 4; ++j)
+      if (a_src[j]) cp_async16(dst + (r_lo + 16 * j) * SK_PITCH, a_src[j] + chunk * SK_KC);
   };
 
   if (PDL) pdl_launch_dependents();

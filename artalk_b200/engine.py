@@ -52,7 +52,8 @@ def smooth_motion(motion: torch.Tensor, clip_length: Optional[int] = None, fix_p
 
 class ARTAvatarInferEngine:
     def __init__(self, load_gaga=False, fix_pose=False, clip_length=750, device="cuda", *, precision="bf16",
-                 state_dict=None, config=None, flame_asset=None, wav2vec=None, make_output_dir=True, lanes=1):
+                 state_dict=None, config=None, flame_asset=None, wav2vec=None, make_output_dir=True, lanes=1,
+                 latency_mode=False):
         if load_gaga:
             raise NotImplementedError("GAGAvatar rendering is outside the audio->motion path (use load_gaga=False)")
         self.device = device
@@ -66,6 +67,8 @@ class ARTAvatarInferEngine:
         configs["AR_CONFIG"]["AUDIO_ENCODER"] = audio_encoder
         self.ARTalk = BitwiseARModel(configs, device=device, precision=precision, wav2vec=wav2vec, lanes=lanes).eval().to(device)
         self.ARTalk.load_state_dict(ckpt, strict=True)
+        if latency_mode:                               # batch-1 / few-clip streaming: see BitwiseARModel.set_latency_mode
+            self.ARTalk.set_latency_mode(True)
         self.flame_model = FLAMEModel(n_shape=300, n_exp=100, scale=1.0, no_lmks=True, asset=flame_asset, device=device)
         self.mesh_renderer = None                      # pytorch3d RenderMesh: rendering is out of scope
         self.output_dir = "render_results/ARTAvatar_{}".format(audio_encoder)

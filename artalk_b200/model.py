@@ -94,6 +94,7 @@ class BitwiseARModel:
         self._streams: List[torch.cuda.Stream] = []
         self._tensors: Dict[str, torch.Tensor] = {}
         self._init_words = None
+        self.latency_rows = 0
 
     # ---- nn.Module look-alikes (inference.py:27-28) -------------------------------------------------
     def eval(self):
@@ -126,6 +127,8 @@ class BitwiseARModel:
                 for name, t in self._tensors.items():
                     _lib.check(lib.artalk_set_tensor(h, name.encode(), t.data_ptr(), code[t.dtype], t.numel()))
                 _lib.check(lib.artalk_finalize(h))
+                if self.latency_rows:
+                    _lib.check(lib.artalk_set_latency_mode(h, self.latency_rows))
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
             torch.cuda.synchronize(dev)
         self._init_words = None
@@ -147,6 +150,13 @@ class BitwiseARModel:
     def set_workspace_limit(self, n_bytes: int):
         for lane in range(len(self._hs)):
             _lib.check(_lib.lib().artalk_set_workspace_limit(self._handle(lane), n_bytes))
+
+    def set_latency_mode(self, on=True, max_rows: int = 128):
+        """Batch-1 / few-clip streaming: GEMMs with at most ``max_rows`` rows take the latency kernel (include/artalk_b200.h,
+        artalk_set_latency_mode). Off (default) = throughput mode, whose arithmetic does not depend on the batch size."""
+        self.latency_rows = int(max_rows) if on else 0
+        for lane in range(len(self._hs)):
+            _lib.check(_lib.lib().artalk_set_latency_mode(self._handle(lane), self.latency_rows))
 
     def enable_graphs(self, on: bool = True):
         for lane in range(len(self._hs)):

@@ -69,6 +69,12 @@ size_t artalk_workspace_bytes(const artalk_engine_t* e);
 /* the body of artalk_ar_chunk is replayed from a CUDA graph after one eager warm-up per (n_clips, teacher forcing);
  * enable = 0 drops the graphs and launches eagerly (default: enabled) */
 int artalk_enable_graphs(artalk_engine_t* e, int enable);
+/* latency mode for batch-1 / few-clip streaming (BASELINE configs[4]; the reference's per-chunk loop, app/models.py:76-115,
+ * run one chunk at a time): max_rows > 0 sends every bf16 GEMM of this engine with at most max_rows rows (and a small output)
+ * to the latency kernel (skinny.cu: 64-row tiles, ~100 CTAs streaming disjoint weight slices) instead of the 128-row tcgen05
+ * tiles; 0 = throughput mode (default), where kernel choice depends only on per-clip shapes so a clip's arithmetic does not
+ * depend on the batch. The two modes differ at bf16 rounding level (fp32 accumulation order). Drops the captured graphs. */
+int artalk_set_latency_mode(artalk_engine_t* e, int max_rows);
 
 /* --- Wav2Vec2Model.forward + multi-scale area pooling (app/modules/wav2vec.py:11-27, app/models.py:93-95) ---
  * audio [n_chunks, chunk_samples] f32 (each row normalised on its own) -> cond [n_chunks, 181, 1024] f32 */

@@ -167,6 +167,36 @@ def test_inference_bf16_free_running(name):
     assert np.median(e0) < MOTION_TOL["bf16"], np.median(e0)        # first chunk: only isolated bit flips
 
 
+def test_latency_mode_within_bf16_tolerance():
+    """artalk_set_latency_mode: at batch 1 every AR / VAE-encoder GEMM (<= 128 rows) takes the skinny kernel. Teacher-forced,
+    the result meets the same oracle tolerances as throughput mode, agrees with it at bf16 rounding level, and streaming
+    equals whole-clip inference inside the mode."""
+    case = CASES["full_10s"]
+    g = gu.load("full_10s")
+    m = model(case.cfg_name, "bf16")
+    gold_words = torch.from_numpy(g["bits"].view(np.int32).copy())
+    gold_prev = torch.from_numpy(g["prev_bits"].view(np.int32).copy())
+    batch = {"audio": case.audio(), "style_motion": case.style()}
+    res = {}
+    for on in (True, False):
+        m.set_latency_mode(on)
+        try:
+            tr = {}
+            for it in range(3):                                  # eager warm-up, capture, replay
+                tr = {}
+                out = m.inference(batch, trace=tr, teacher_words=gold_words, teacher_prev_words=gold_prev)
+            free = m.inference(batch)
+        finally:
+            m.set_latency_mode(False)
+        res[on] = (tr["logits"].float().cpu(), out.cpu(), free.cpu())
+    err = np.abs(res[True][0].numpy() - g["logits"])
+    assert err.max() < 0.6 and err.mean() < 0.04, (err.max(), err.mean())
+    assert np.abs(res[True][1].numpy() - g["motion"]).max() < MOTION_TOL["bf16"]
+    d = (res[True][0] - res[False][0]).abs()
+    assert d.max().item() < 0.3 and d.mean().item() < 0.02, (d.max().item(), d.mean().item())
+    assert torch.isfinite(res[True][2]).all() and res[True][2].shape == res[False][2].shape
+
+
 def test_whole_stack_kernel_matches_separate_kernels():
     """Opt-in (option ar_small = 1): the few-token scale steps (1 and 5 new tokens per clip) run every AR block + the head
     in ONE cooperative launch (skinny.cu::ar_small_kernel, grid-wide barriers between phases). Teacher-forced with the same bits, its logits agree with
@@ -333,8 +363,8 @@ def test_engine_surface_matches_reference_golden():
         eng.rendering(None, out)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_streaming_session_equals_whole_clip(precision, tmp_path):
+@pytest.mark.parametrize("precision,latency", [("fp32", False), ("bf16", False), ("bf16", True)])
+def test_streaming_session_equals_whole_clip(precision, latency, tmp_path):
     """audio pushed in ragged pieces (chunk arrives -> encode -> AR) gives the whole-clip result; WAV file
     ingestion (48 kHz stereo -> 16 kHz mono on the device) and the (T,106) .pt motion file round trip."""
     import struct
@@ -343,7 +373,8 @@ def test_streaming_session_equals_whole_clip(precision, tmp_path):
     cfg = config.TINY
     eng = ARTAvatarInferEngine(load_gaga=False, clip_length=750, device=DEV, precision=precision,
                                state_dict=gu.state_dict("TINY"), config=cfg.to_reference_json(),
-                               flame_asset=synthetic.make_flame_asset(0), wav2vec=cfg.wav2vec, make_output_dir=False)
+                               flame_asset=synthetic.make_flame_asset(0), wav2vec=cfg.wav2vec, make_output_dir=False,
+                               latency_mode=latency)
     eng.output_dir = str(tmp_path)
     eng.set_style_motion(synthetic.make_style_motion(1)[0])
     S = 2 * cfg.chunk_samples + 12345                      # 2 full chunks + a ragged third

@@ -12,13 +12,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--chunks", type=int, default=40); ap.add_argument("--precision", default="bf16")
 ap.add_argument("--clips", type=int, default=1); ap.add_argument("--config", default="FULL")
 ap.add_argument("--no-mesh", action="store_true")
+ap.add_argument("--latency-rows", type=int, default=128, help="row cap of the latency kernels (artalk_set_latency_mode)")
+ap.add_argument("--throughput-mode", action="store_true", help="keep the batch-invariant throughput kernels (no latency mode)")
 a = ap.parse_args()
 cfg = getattr(config, a.config)
 dev = torch.device("cuda:0")
 eng = ARTAvatarInferEngine(load_gaga=False, device=str(dev), precision=a.precision, state_dict=synthetic.make_state_dict(cfg, 0),
                            config=cfg.to_reference_json(), flame_asset=synthetic.make_flame_asset(0), wav2vec=cfg.wav2vec,
-                           make_output_dir=False)
+                           make_output_dir=False, latency_mode=not a.throughput_mode)
 m = eng.ARTalk
+if not a.throughput_mode:
+    m.set_latency_mode(True, a.latency_rows)
 B = a.clips
 audio = synthetic.make_audio(B, cfg.chunk_samples * a.chunks).pin_memory()
 style = m.style_cond(synthetic.make_style_motion(B), B)
@@ -43,7 +47,7 @@ for c in range(a.chunks):
 lat.sort()
 p = lambda q: lat[min(len(lat) - 1, int(q * len(lat)))]
 med = lambda i: sorted(x[i] for x in parts)[len(parts) // 2]
-print(json.dumps({"mode": "latency", "clips": B, "precision": a.precision, "chunks_timed": len(lat),
+print(json.dumps({"mode": "latency", "latency_kernels": not a.throughput_mode, "clips": B, "precision": a.precision, "chunks_timed": len(lat),
                   "p50_ms_per_4s_chunk": p(0.5), "p90_ms_per_4s_chunk": p(0.9), "p50_ms_per_2s": p(0.5) / 2,
                   "p50_parts_ms": {"h2d+wav2vec": med(0), "ar+vae": med(1), "flame+d2h": med(2)},
                   "frames_per_sec": B * 100 / (p(0.5) / 1e3), "mesh": not a.no_mesh}))
