@@ -191,12 +191,22 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
 #pragma unroll
       for (int j = 0; j < 8; ++j) rpre[j] = *(reinterpret_cast<const float4*>(p.resid + r_off + col0) + j);
     }
+    // plain epilogue (registers to spare): the bias row is requested ahead of the accumulator read as well
+    float4 bpre[8];
+    const bool pre_b = EPI == 0 && bias != nullptr && full;
+    if (pre_b) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bpre[j] = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
+    }
     float v[32];
     tmem_ld32(taddr, v);
     if (!full && !live) return;                                  // ragged path below is per thread (no warp collectives)
     // ---- bias
     if (bias) {
-      if (full) {
+      if (pre_b) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[4 * j] += bpre[j].x; v[4 * j + 1] += bpre[j].y; v[4 * j + 2] += bpre[j].z; v[4 * j + 3] += bpre[j].w; }
+      } else if (full) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));

@@ -87,22 +87,35 @@ __global__ void __launch_bounds__(128) adaln_kernel(float* __restrict__ x, const
   if (row >= rows) return;
   float* xr = x + (int64_t)row * C;
   const TA* ar = ada + ada_map.off(row);
-  float v[V4][4];
-  float s = 0.f;
+  float v[V4][4], sc[V4][4], sh[V4][4];
+  // every operand of the row is requested before the first reduction: for the few-row launches of the recurrence this kernel
+  // is one memory round trip (x, y, gate, scale, shift together) instead of two dependent ones
 #pragma unroll
   for (int i = 0; i < V4; ++i) {
     const int c = (i * 32 + lane) * 4;
     load4(xr + c, v[i]);
-    if (y) {
-      float yv[4], gv[4];
-      load4(y + (int64_t)row * C + c, yv);
-      load4(ar + gate_off + c, gv);
+    load4(ar + scale_off + c, sc[i]);
+    load4(ar + shift_off + c, sh[i]);
+  }
+  float s = 0.f;
+  if (y) {
+    float yv[V4][4], gv[V4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = fmaf(yv[j], gv[j], v[i][j]);
+    for (int i = 0; i < V4; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      load4(y + (int64_t)row * C + c, yv[i]);
+      load4(ar + gate_off + c, gv[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      const int c = (i * 32 + lane) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = fmaf(yv[i][j], gv[i][j], v[i][j]);
       store4(xr + c, v[i]);
     }
-    s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
   }
+#pragma unroll
+  for (int i = 0; i < V4; ++i) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
   float mean = warp_sum(s) * (1.0f / C);
   float q = 0.f;
 #pragma unroll
@@ -114,11 +127,9 @@ __global__ void __launch_bounds__(128) adaln_kernel(float* __restrict__ x, const
 #pragma unroll
   for (int i = 0; i < V4; ++i) {
     int c = (i * 32 + lane) * 4;
-    float sc[4], sh[4], o[4];
-    load4(ar + scale_off + c, sc);
-    load4(ar + shift_off + c, sh);
+    float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mean) * rstd * (1.0f + sc[j]) + sh[j];
+    for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mean) * rstd * (1.0f + sc[i][j]) + sh[i][j];
     store4(orow + c, o);
   }
 }
