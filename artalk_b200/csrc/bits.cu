@@ -83,29 +83,28 @@ __global__ void __launch_bounds__(256) bits_tokens_kernel(BitsTables tb, const u
     __syncthreads();
     if (n < C) {
       const int row0 = tb.cum[q - 1];
-      // 4 rows per iteration with their position-embedding loads issued up front: one dependent L2 round trip per row made
-      // this loop (up to 100 rows) the whole cost of the kernel
-      int r = 0;
-      for (; r + 4 <= pq; r += 4) {
-        float pv[4], a[4];
+      // the position-embedding loads (one L2 round trip each, independent of everything else) are the latency of this loop:
+      // groups of 16 rows, the next group's loads in flight while the current group's 16 x 32 FMAs run
+      constexpr int G = 16;
+      float pv[G];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) pv[u] = __ldg(pos + (int64_t)(row0 + r + u) * C + n);
+      for (int u = 0; u < G; ++u) pv[u] = (u < pq) ? __ldg(pos + (int64_t)(row0 + u) * C + n) : 0.f;
+      for (int r = 0; r < pq; r += G) {
+        float nx[G];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          a[u] = be;
+        for (int u = 0; u < G; ++u) nx[u] = (r + G + u < pq) ? __ldg(pos + (int64_t)(row0 + r + G + u) * C + n) : 0.f;
 #pragma unroll
-          for (int c = 0; c < CD; ++c) a[u] = fmaf(feat[r + u][c], w[c], a[u]);
-          a[u] += pv[u];
+        for (int u = 0; u < G; ++u) {
+          if (r + u < pq) {
+            float a = be;
+#pragma unroll
+            for (int c = 0; c < CD; ++c) a = fmaf(feat[r + u][c], w[c], a);
+            a += pv[u];
+            oc[(int64_t)(row0 - base_row + r + u) * C + n] = from_f32<TO>(a);
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) oc[(int64_t)(row0 - base_row + r + u) * C + n] = from_f32<TO>(a[u]);
-      }
-      for (; r < pq; ++r) {
-        float a = be;
-#pragma unroll
-        for (int c = 0; c < CD; ++c) a = fmaf(feat[r][c], w[c], a);
-        a += pos[(int64_t)(row0 + r) * C + n];
-        oc[(int64_t)(row0 - base_row + r) * C + n] = from_f32<TO>(a);
+        for (int u = 0; u < G; ++u) pv[u] = nx[u];
       }
     }
     __syncthreads();

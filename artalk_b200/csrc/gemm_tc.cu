@@ -32,6 +32,7 @@ struct TcParams {
   // tail split: the last (partial) wave's tiles [main_tiles, main_tiles + r) are cut into `tail_split` column slices of
   // `tail_bn` columns each, so the ragged wave costs tail_bn/BN of a full one (total_tiles counts the slices)
   int main_tiles, tail_split, tail_bn;
+  int band_n;              // pair kernel: > 0 = N tiles per L2 band (see decode)
   int tma_resid;           // pair kernel, EPI 1: the fp32 residual tile arrives by TMA (plain [M, N] residual, N % 32 == 0)
   int num_kb;              // K blocks of 64
   int tap_mode, tap_pad;   // tap mode: k-block j reads rows shifted by (j - tap_pad), columns of group g
@@ -657,8 +658,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       sub = u - (u / p.tail_split) * p.tail_split;
       bn = p.tail_bn;
     }
-    const int n_idx = big % p.n_tiles_n;
-    const int rest = big / p.n_tiles_n;
+    int n_idx, rest;
+    if (p.band_n > 0) {
+      // W too large for L2 (the hoisted AdaLN GEMM: 116 MB): N is walked in bands of band_n tiles, all M tiles per band, so a
+      // band of W (<= 32 MB) stays L2-resident while the (small) A matrix is re-read per band. Plain N-fastest order
+      // streamed the whole W from HBM once per M tile: 5.3 GB per launch, 1100 TFLOP/s
+      const int m_all = p.tiles_per_batch * p.n_batches, per_band = p.band_n * m_all;
+      int band = big / per_band;
+      const int n_bands = (p.n_tiles_n + p.band_n - 1) / p.band_n;
+      if (band > n_bands - 1) band = n_bands - 1;
+      const int r = big - band * per_band;
+      const int width = (band == n_bands - 1) ? p.n_tiles_n - band * p.band_n : p.band_n;
+      rest = r / width;
+      n_idx = band * p.band_n + (r - rest * width);
+    } else {
+      n_idx = big % p.n_tiles_n;
+      rest = big / p.n_tiles_n;
+    }
     mt = rest % p.tiles_per_batch;
     b = rest / p.tiles_per_batch;
     col_base = n_idx * BN + sub * p.tail_bn;
@@ -882,6 +898,7 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
 }
 int g_pair_mode = 1;      // 0: never use the CTA-pair kernel (developer switch, ARTALK_GEMM_PAIR=0)
 int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
+int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
 }  // namespace
@@ -889,6 +906,7 @@ int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (
 void set_gemm_pair_mode(int on) { g_pair_mode = on; }
 void set_gemm_force_bn(int bn) { g_force_bn = bn; }
 void set_gemm_tma_resid(int on) { g_tma_resid = on; }
+void set_gemm_band_mb(int mb) { g_band_mb = mb; }
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AT_OK;
@@ -908,7 +926,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     AT_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   TcParams p;
-  p.tma_resid = 0;
+  p.tma_resid = 0; p.band_n = 0;
   p.N = g.N;
   const bool batched = g.a_map.rpb > 0;
   p.rpb = batched ? g.a_map.rpb : g.M;
@@ -927,6 +945,10 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     const double waves_eff = (double)(tiles2 / n_cl) + (rem2 ? (split2 > 1 ? 1.3 / split2 : 1.0) : 0.0);
     if (tiles2 >= 4L * n_cl && (double)tiles2 / (waves_eff * n_cl) >= 0.85 && row_eff >= 0.85 && tiles2 < (1L << 30)) {
       p.tiles_per_batch = tpb2; p.n_tiles_n = n_tiles_n2; p.groups = 1;
+      if (g_band_mb > 0 && (double)g.N * g.K * 2.0 > 2.0 * g_band_mb * 1048576.0) {
+        const int bn_tiles = (int)((double)g_band_mb * 1048576.0 / (256.0 * g.K * 2.0));
+        p.band_n = bn_tiles < 1 ? 1 : bn_tiles;
+      }
       p.main_tiles = (int)tiles2 - (split2 > 1 ? rem2 : 0); p.tail_split = split2; p.tail_bn = 256 / split2;
       p.total_tiles = p.main_tiles + (split2 > 1 ? rem2 * split2 : 0);
       p.num_kb = ceil_div(g.K, BK);

@@ -75,6 +75,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
 void set_gemm_pair_mode(int on);
 void set_gemm_force_bn(int bn);
 void set_gemm_tma_resid(int on);
+void set_gemm_band_mb(int mb);
 // skinny-M bf16 GEMM (mma.sync, cp.async ring; M <= option "skinny_max_m") for the latency-bound steps. skinny.cu
 bool gemm_skinny_supported(const GemmArgs& g);
 int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st);
@@ -97,7 +98,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t st);
 bool attention_tc_supported(const AttnArgs& a);
 void set_attn_simt_max_lq(int v);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
-// bf16, head_dim 64, <= 8 query rows, <= 384 keys, no split mask: one CTA per (sequence, head). skinny.cu
+// bf16, head_dim 64, <= 8 query rows, <= 256 keys, no split mask: one CTA per (sequence, head). skinny.cu
 bool attention_few_supported(const AttnArgs& a);
 int launch_attention_few(const AttnArgs& a, cudaStream_t st);
 void set_attn_few_max_lq(int v);

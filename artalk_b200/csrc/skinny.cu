@@ -12,8 +12,8 @@
 //    shared memory, and one generic epilogue pass over the fp32 tile (bias, activation, gate, residual, fp32 / bf16 outputs
 //    through row maps, or the fused AR q/k/v head normalisation + KV-cache scatter of app/transformer.py:68-74).
 //    Weights do not depend on the previous kernel: their first ring fill is issued before griddepcontrol.wait (PDL).
-//  * attn_few_kernel: softmax(q k^T) v for <= 8 query rows per (clip, head) and <= 384 resident keys
-//    (app/transformer.py:75-77 in the KV-cached schedule: no mask). One 128-thread CTA per (clip, head): a thread scores
+//  * attn_few_kernel: softmax(q k^T) v for <= 8 query rows per (clip, head) and <= 256 resident keys
+//    (app/transformer.py:75-77 in the KV-cached schedule: no mask). One 256-thread CTA per (clip, head): a thread scores
 //    whole key rows (8 x 16-byte loads in flight per thread), warps reduce the softmax, and the P V product reads V as
 //    16-byte pieces with 4 keys per warp instruction. It is an HBM-streaming kernel (36 MB of K/V per launch at 64 clips).
 //
@@ -396,13 +396,16 @@ int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st) {
 
 // ---------------------------------------------------------------- few-query attention
 namespace {
-constexpr int AF_MAXQ = 8, AF_MAXK = 384, AF_THREADS = 128;
+constexpr int AF_MAXQ = 8, AF_MAXK = 256, AF_THREADS = 256;
 
 template <int LQ>
 __global__ void __launch_bounds__(AF_THREADS) attn_few_kernel(const AttnArgs a) {
+  // The kernel is one memory round trip: every K row (one per thread) and every V piece (4 key rows per warp instruction,
+  // 8 instructions per warp) is requested into registers up front; scores, softmax and P V then run out of registers and
+  // shared memory. (A first version loaded V after the softmax in dependent batches: 19.6 us against a 6 us DRAM floor.)
   __shared__ float qs[LQ][64];
   __shared__ float sc[LQ][AF_MAXK];
-  __shared__ float part[4][LQ][64];
+  __shared__ float part[AF_THREADS / 32][LQ][64];
   __shared__ float inv[LQ];
   pdl_enter();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -411,23 +414,29 @@ __global__ void __launch_bounds__(AF_THREADS) attn_few_kernel(const AttnArgs a) 
   const bf16* qb = reinterpret_cast<const bf16*>(a.q) + (int64_t)seq * a.q_ss + head * 64;
   const bf16* kb = reinterpret_cast<const bf16*>(a.k) + (int64_t)seq * a.k_ss + head * 64;
   const bf16* vb = reinterpret_cast<const bf16*>(a.v) + (int64_t)seq * a.v_ss + head * 64;
+  const int ksub = lane >> 3, dg = lane & 7;
+  constexpr int VIT = AF_MAXK / AF_THREADS * 8;             // V iterations: 32 key rows per iteration over the CTA
+  uint4 vraw[VIT], kraw[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) kraw[c] = tid < lk ? __ldg(reinterpret_cast<const uint4*>(kb + (int64_t)tid * a.k_rs) + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int it = 0; it < VIT; ++it) {
+    const int j = it * (AF_THREADS / 8) + warp * 4 + ksub;
+    vraw[it] = j < lk ? __ldg(reinterpret_cast<const uint4*>(vb + (int64_t)j * a.v_rs + dg * 8)) : make_uint4(0, 0, 0, 0);
+  }
   for (int i = tid; i < lq * 64; i += AF_THREADS) {
     const int r = i >> 6, d = i & 63;
     qs[r][d] = __bfloat162float(qb[(int64_t)r * a.q_rs + d]) * a.scale;
   }
   __syncthreads();
   // ---- scores: one key row per thread
-  for (int j = tid; j < lk; j += AF_THREADS) {
-    const uint4* kp = reinterpret_cast<const uint4*>(kb + (int64_t)j * a.k_rs);
-    uint4 raw[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) raw[c] = __ldg(kp + c);
+  if (tid < lk) {
     float s[LQ];
 #pragma unroll
     for (int i = 0; i < LQ; ++i) s[i] = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint32_t w[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+      const uint32_t w[4] = {kraw[c].x, kraw[c].y, kraw[c].z, kraw[c].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
@@ -440,11 +449,11 @@ __global__ void __launch_bounds__(AF_THREADS) attn_few_kernel(const AttnArgs a) 
     }
 #pragma unroll
     for (int i = 0; i < LQ; ++i)
-      if (i < lq) sc[i][j] = s[i];
+      if (i < lq) sc[i][tid] = s[i];
   }
   __syncthreads();
-  // ---- softmax: warp w owns query rows w, w + 4
-  for (int i = warp; i < lq; i += 4) {
+  // ---- softmax: one query row per warp
+  for (int i = warp; i < lq; i += AF_THREADS / 32) {
     float m = -INFINITY;
     for (int j = lane; j < lk; j += 32) m = fmaxf(m, sc[i][j]);
     m = warp_max(m);
@@ -458,19 +467,17 @@ __global__ void __launch_bounds__(AF_THREADS) attn_few_kernel(const AttnArgs a) 
     if (lane == 0) inv[i] = 1.0f / sum;
   }
   __syncthreads();
-  // ---- P V: a warp instruction reads 4 key rows x 128 B (lane -> key lane/8, dims (lane%8)*8 .. +8)
-  const int ksub = lane >> 3, dg = lane & 7;
+  // ---- P V out of the registers (lane -> key lane/8 of the warp's 4, dims (lane%8)*8 .. +8)
   float acc[LQ][8];
 #pragma unroll
   for (int i = 0; i < LQ; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-#pragma unroll 2
-  for (int j0 = warp * 4; j0 < lk; j0 += 16) {
-    const int j = j0 + ksub;
+#pragma unroll
+  for (int it = 0; it < VIT; ++it) {
+    const int j = it * (AF_THREADS / 8) + warp * 4 + ksub;
     if (j < lk) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(vb + (int64_t)j * a.v_rs + dg * 8));
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      const uint32_t w[4] = {vraw[it].x, vraw[it].y, vraw[it].z, vraw[it].w};
       float vv[8];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -503,8 +510,9 @@ __global__ void __launch_bounds__(AF_THREADS) attn_few_kernel(const AttnArgs a) 
   bf16* ob = reinterpret_cast<bf16*>(a.out) + (int64_t)seq * a.o_ss + head * 64;
   for (int i = tid; i < lq * 32; i += AF_THREADS) {
     const int r = i >> 5, d = (i & 31) * 2;
-    const float s0 = (part[0][r][d] + part[1][r][d]) + (part[2][r][d] + part[3][r][d]);
-    const float s1 = (part[0][r][d + 1] + part[1][r][d + 1]) + (part[2][r][d + 1] + part[3][r][d + 1]);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < AF_THREADS / 32; ++w) { s0 += part[w][r][d]; s1 += part[w][r][d + 1]; }
     *reinterpret_cast<__nv_bfloat162*>(ob + (int64_t)r * a.o_rs + d) = __floats2bfloat162_rn(s0 * inv[r], s1 * inv[r]);
   }
 }

@@ -96,6 +96,27 @@ def test_gemm_cta_pair_kernel(M, N, K, act, resid, gated):
         assert (out.float() - ref).abs().max().item() < (tol + 8e-3) * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K", [(9700, 2048, 512), (18944, 1280, 1024), (9472, 2304, 256)])
+def test_gemm_cta_pair_kernel_l2_bands(M, N, K):
+    """Weights larger than L2 (the hoisted AdaLN GEMM, 116 MB) are walked in N bands so that a band of W stays L2-resident.
+    Forced here with a 1 MB band: even bands, a narrower last band (5 N tiles in bands of 2) and a single band, with the ragged
+    last wave cut into column slices on top."""
+    dt, tol = torch.bfloat16, 3e-2
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    A = torch.randn(M, K, generator=g).to(dev(), dt)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev(), dt)
+    b = torch.randn(N, generator=g).to(dev())
+    ref = (A.double() @ W.double().t() + b.double()).float()
+    _lib.check(_lib.lib().artalk_set_option(b"gemm_band_mb", 1))
+    try:
+        out = torch.full((M, N), float("nan"), device=dev(), dtype=dt)
+        run_gemm(1, A, W, M, N, K, bias=b, out_act=out)
+    finally:
+        _lib.check(_lib.lib().artalk_set_option(b"gemm_band_mb", 32))
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < (tol + 8e-3) * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("M,N,K,act,mode", [(64, 768, 3072, 0, "f32"), (64, 3072, 768, 2, "bf16"), (320, 768, 3072, 0, "f32"),
                                              (320, 3072, 768, 2, "bf16"), (1, 768, 768, 0, "f32"), (5, 64, 768, 0, "rows"),
                                              (100, 2304, 768, 1, "dual"), (200, 512, 512, 3, "resid"), (257, 1536, 512, 0, "bf16"),
@@ -224,7 +245,7 @@ def run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, scale, split=0):
 @pytest.mark.parametrize("dt,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("n_seq,H,D,lq,lk,split", [(3, 16, 64, 199, 199, 0), (2, 8, 64, 200, 200, 100), (4, 12, 64, 25, 212, 0),
                                                    (5, 12, 64, 1, 182, 0), (2, 4, 32, 50, 50, 0), (2, 12, 64, 100, 362, 0),
-                                                   (7, 12, 64, 5, 187, 0), (3, 12, 64, 8, 384, 0), (2, 8, 64, 3, 17, 0)])
+                                                   (7, 12, 64, 5, 187, 0), (3, 12, 64, 8, 256, 0), (2, 8, 64, 3, 17, 0)])
 def test_attention(dt, tol, n_seq, H, D, lq, lk, split):
     g = torch.Generator(device="cpu").manual_seed(lq * 3 + lk)
     Cw = H * D

@@ -17,6 +17,8 @@ eng = ARTAvatarInferEngine(load_gaga=False, device=dev, precision="bf16", state_
                            config=cfg.to_reference_json(), flame_asset=synthetic.make_flame_asset(0), wav2vec=cfg.wav2vec,
                            make_output_dir=False)
 m = eng.ARTalk
+if os.environ.get("ARTALK_WS_LIMIT_MB"):          # developer switch: smaller wav2vec sub-batches (activations closer to L2 size)
+    m.set_workspace_limit(int(os.environ["ARTALK_WS_LIMIT_MB"]) << 20)
 B = a.clips
 S = int(a.seconds * 16000)
 n_chunks = cfg.chunks_for_samples(S)
