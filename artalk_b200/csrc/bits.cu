@@ -47,6 +47,13 @@ __global__ void __launch_bounds__(256) bits_tokens_kernel(BitsTables tb, const u
   const int base_row = q_lo ? tb.cum[q_lo - 1] : 0;
   const int rows_per_clip = tb.cum[q_hi] - base_row;
   TO* oc = out + (int64_t)clip * rows_per_clip * C;
+  // operator tables -> shared memory in one round trip (read per element from global they were a chain of dependent L2
+  // loads in every level's loops: 72 us for the 181-token launch)
+  __shared__ int s_i0[8 * MAXT / 2], s_i1[8 * MAXT / 2], s_ps[8 * MAXT / 2], s_pe[8 * MAXT / 2];
+  __shared__ float s_w1[8 * MAXT / 2];
+  for (int i = tid; i < (q_hi + 1) * T; i += blockDim.x) {
+    s_i0[i] = tb.up_i0[i]; s_i1[i] = tb.up_i1[i]; s_w1[i] = tb.up_w1[i]; s_ps[i] = tb.pool_start[i]; s_pe[i] = tb.pool_end[i];
+  }
   for (int i = tid; i < tb.L; i += blockDim.x) sw[i] = words[(int64_t)clip * words_cs + i];
   for (int i = tid; i < T * CD; i += blockDim.x) (&f_hat[0][0])[i] = 0.f;
   float w[CD];
@@ -66,8 +73,8 @@ __global__ void __launch_bounds__(256) bits_tokens_kernel(BitsTables tb, const u
     const int lvl = q - 1, src0 = lvl ? tb.cum[lvl - 1] : 0;
     for (int i = tid; i < T * CD; i += blockDim.x) {
       int t = i >> 5, c = i & 31;
-      int i0 = tb.up_i0[lvl * T + t], i1 = tb.up_i1[lvl * T + t];
-      float w1 = tb.up_w1[lvl * T + t], w0 = 1.0f - w1;
+      int i0 = s_i0[lvl * T + t], i1 = s_i1[lvl * T + t];
+      float w1 = s_w1[lvl * T + t], w0 = 1.0f - w1;
       f_hat[t][c] += w0 * bit_val(sw[src0 + i0], c) + w1 * bit_val(sw[src0 + i1], c);
     }
     __syncthreads();
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(256) bits_tokens_kernel(BitsTables tb, const u
     const int pq = tb.pn[q];
     for (int i = tid; i < pq * CD; i += blockDim.x) {
       int r = i >> 5, c = i & 31;
-      int s = tb.pool_start[q * T + r], e = tb.pool_end[q * T + r];
+      int s = s_ps[q * T + r], e = s_pe[q * T + r];
       float a = 0.f;
       for (int t = s; t < e; ++t) a += f_hat[t][c];
       feat[r][c] = a / (float)(e - s);
@@ -115,7 +122,8 @@ int launch_bits_tokens(const BitsTables& tb, const uint32_t* words, int64_t word
                        const float* embed_w, const float* embed_b, const float* pos, void* out, int out_dt,
                        int n_clips, int q_lo, int q_hi, int C, cudaStream_t st) {
   if (n_clips <= 0) return AT_OK;
-  AT_REQUIRE(tb.T <= MAXT && tb.L <= 256 && q_lo >= 0 && q_hi < tb.n_levels && q_lo <= q_hi, "bits_tokens: bad levels");
+  AT_REQUIRE(tb.T <= MAXT && tb.L <= 256 && q_lo >= 0 && q_hi < tb.n_levels && q_lo <= q_hi && tb.n_levels * tb.T <= 8 * MAXT / 2,
+             "bits_tokens: bad levels");
   dim3 grid(n_clips, ceil_div(C, 256));
   if (out_dt == DT_F32)
     AT_CUDA(launch_k(bits_tokens_kernel<float>, dim3(grid), dim3(256), 0, st, tb, words, words_cs, style, embed_w, embed_b, pos, (float*)out, q_lo, q_hi, C));
@@ -131,16 +139,19 @@ __global__ void __launch_bounds__(256) bits_latent_kernel(BitsTables tb, const u
                                                           const float* __restrict__ dec_pos, TO* __restrict__ out, int half) {
   pdl_enter();
   __shared__ uint32_t sw[256];
+  __shared__ int s_i0[8 * MAXT / 2], s_i1[8 * MAXT / 2];
+  __shared__ float s_w1[8 * MAXT / 2];
   const int clip = blockIdx.x, tid = threadIdx.x, T = tb.T;
   for (int i = tid; i < tb.L; i += blockDim.x) sw[i] = words[(int64_t)clip * words_cs + i];
+  for (int i = tid; i < (tb.n_levels - 1) * T; i += blockDim.x) { s_i0[i] = tb.up_i0[i]; s_i1[i] = tb.up_i1[i]; s_w1[i] = tb.up_w1[i]; }
   __syncthreads();
   for (int i = tid; i < T * CD; i += blockDim.x) {
     int t = i >> 5, c = i & 31;
     float f = 0.f;
     for (int lvl = 0; lvl + 1 < tb.n_levels; ++lvl) {
       int src0 = lvl ? tb.cum[lvl - 1] : 0;
-      int i0 = tb.up_i0[lvl * T + t], i1 = tb.up_i1[lvl * T + t];
-      float w1 = tb.up_w1[lvl * T + t], w0 = 1.0f - w1;
+      int i0 = s_i0[lvl * T + t], i1 = s_i1[lvl * T + t];
+      float w1 = s_w1[lvl * T + t], w0 = 1.0f - w1;
       f += w0 * bit_val(sw[src0 + i0], c) + w1 * bit_val(sw[src0 + i1], c);
     }
     f += bit_val(sw[tb.cum[tb.n_levels - 2] + t], c);
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(256) bits_latent_kernel(BitsTables tb, const u
 int launch_bits_latent(const BitsTables& tb, const uint32_t* words, int64_t words_cs, const float* dec_pos, void* out,
                        int out_dt, int n_clips, int half, cudaStream_t st) {
   if (n_clips <= 0) return AT_OK;
-  AT_REQUIRE(tb.L <= 256 && tb.n_levels >= 2, "bits_latent: bad tables");
+  AT_REQUIRE(tb.L <= 256 && tb.n_levels >= 2 && tb.n_levels * tb.T <= 8 * MAXT / 2, "bits_latent: bad tables");
   if (out_dt == DT_F32) AT_CUDA(launch_k(bits_latent_kernel<float>, dim3(n_clips), dim3(256), 0, st, tb, words, words_cs, dec_pos, (float*)out, half));
   else AT_CUDA(launch_k(bits_latent_kernel<bf16>, dim3(n_clips), dim3(256), 0, st, tb, words, words_cs, dec_pos, (bf16*)out, half));
   AT_LAUNCH_CHECK();
@@ -167,6 +178,11 @@ __global__ void __launch_bounds__(256) bsq_kernel(BitsTables tb, const float* __
   __shared__ float qs[MAXT][CD];
   const int clip = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = tb.T;
   const float q_scale = 0.17677669529663687f;
+  __shared__ int s_i0[8 * MAXT / 2], s_i1[8 * MAXT / 2], s_ps[8 * MAXT / 2], s_pe[8 * MAXT / 2];
+  __shared__ float s_w1[8 * MAXT / 2];
+  for (int i = tid; i < tb.n_levels * T; i += blockDim.x) {   // operator tables: one round trip instead of one per element
+    s_i0[i] = tb.up_i0[i]; s_i1[i] = tb.up_i1[i]; s_w1[i] = tb.up_w1[i]; s_ps[i] = tb.pool_start[i]; s_pe[i] = tb.pool_end[i];
+  }
   for (int i = tid; i < T * CD; i += blockDim.x) (&r[0][0])[i] = enc_out[(int64_t)clip * T * CD + i];
   __syncthreads();
   for (int k = 0; k < tb.n_levels; ++k) {
@@ -175,7 +191,7 @@ __global__ void __launch_bounds__(256) bsq_kernel(BitsTables tb, const float* __
       float a;
       if (pt == T) a = r[i][lane];
       else {
-        int s = tb.pool_start[k * T + i], e = tb.pool_end[k * T + i];
+        int s = s_ps[k * T + i], e = s_pe[k * T + i];
         a = 0.f;
         for (int t = s; t < e; ++t) a += r[t][lane];
         a = a / (float)(e - s);
@@ -195,8 +211,8 @@ __global__ void __launch_bounds__(256) bsq_kernel(BitsTables tb, const float* __
         float up;
         if (pt == T) up = qs[t][c];
         else {
-          int i0 = tb.up_i0[k * T + t], i1 = tb.up_i1[k * T + t];
-          float w1 = tb.up_w1[k * T + t], w0 = 1.0f - w1;
+          int i0 = s_i0[k * T + t], i1 = s_i1[k * T + t];
+          float w1 = s_w1[k * T + t], w0 = 1.0f - w1;
           up = w0 * qs[i0][c] + w1 * qs[i1][c];
         }
         r[t][c] -= up;
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(256) bsq_kernel(BitsTables tb, const float* __
 int launch_bsq_quantize(const BitsTables& tb, const float* enc_out, uint32_t* words, int64_t words_cs, int n_clips,
                         cudaStream_t st) {
   if (n_clips <= 0) return AT_OK;
-  AT_REQUIRE(tb.T <= MAXT, "bsq: T too large");
+  AT_REQUIRE(tb.T <= MAXT && tb.n_levels * tb.T <= 8 * MAXT / 2, "bsq: T too large");
   AT_CUDA(launch_k(bsq_kernel, dim3(n_clips), dim3(256), 0, st, tb, enc_out, words, words_cs));
   AT_LAUNCH_CHECK();
   return AT_OK;
