@@ -91,7 +91,9 @@ class ARTAvatarInferEngine:
 
     def inference_batch(self, audio, style_motion=None, clip_length=None):
         """Batched form: audio (B,S), style_motion (B,50,106) or None -> (B, T, 106); equals the per-clip loop."""
-        pred = self.ARTalk.inference({"audio": audio.to(self.device), "style_motion": style_motion}, with_gtmotion=False)
+        if not (audio.device.type == "cpu" and audio.is_pinned()):      # pinned host audio is uploaded by the model itself,
+            audio = audio.to(self.device)                               # overlapped with the style encoder
+        pred = self.ARTalk.inference({"audio": audio, "style_motion": style_motion}, with_gtmotion=False)
         clip_length = clip_length if clip_length is not None else self.clip_length
         return smooth_motion(pred, clip_length, self.fix_pose)
 

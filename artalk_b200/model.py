@@ -95,6 +95,7 @@ class BitwiseARModel:
         self._tensors: Dict[str, torch.Tensor] = {}
         self._init_words = None
         self.latency_rows = 0
+        self._copy_stream = None
 
     # ---- nn.Module look-alikes (inference.py:27-28) -------------------------------------------------
     def eval(self):
@@ -169,7 +170,8 @@ class BitwiseARModel:
 
     # ---- stage-level calls (each is one C-ABI call on the current stream) ------------------------------
     def _dev(self, t, dtype=torch.float32):
-        return t.to(self._device, dtype).contiguous()
+        pinned = t.device.type == "cpu" and t.is_pinned()
+        return t.to(self._device, dtype, non_blocking=pinned).contiguous()
 
     def audio_cond(self, chunks: torch.Tensor, lane: int = 0) -> torch.Tensor:
         """(N, 64000) audio chunks -> (N, 181, 1024) conditioning (wav2vec2 + area pooling)."""
@@ -224,14 +226,16 @@ class BitwiseARModel:
             _lib.ptr(words_out), _lib.ptr(logits_out), _lib.ptr(forced_words), _lib.ptr(enc_out), _lib.stream_ptr(self._device)))
 
     # ---- app/models.py:62-121 -------------------------------------------------------------------------
-    def _run_clips(self, audio, style_motion, motion, b0, b1, lane, trace, teacher_words, teacher_prev_words):
+    def _run_clips(self, audio, style_motion, motion, b0, b1, lane, trace, teacher_words, teacher_prev_words, audio_ready=None):
         """Full pipeline for clips [b0, b1) on the current stream with lane ``lane``'s engine; writes motion[b0:b1]."""
         cfg = self.cfg
         T, n_chunks = cfg.chunk_frames, motion.shape[1]
         nb = b1 - b0
+        style = self.style_cond(None if style_motion is None else style_motion[b0:b1], nb, lane)
+        if audio_ready is not None:                       # audio upload in flight on the copy stream (see inference)
+            torch.cuda.current_stream(self._device).wait_event(audio_ready)
         cond = self.audio_cond(audio[b0:b1].reshape(nb * n_chunks, cfg.chunk_samples), lane).view(
             nb, n_chunks, cfg.seq_tokens, cfg.cond_dim)
-        style = self.style_cond(None if style_motion is None else style_motion[b0:b1], nb, lane)
         if trace is not None:
             trace["cond"][b0:b1].copy_(cond); trace["style"][b0:b1].copy_(style)
         for g0 in range(0, nb, self.max_clips):
@@ -277,10 +281,26 @@ class BitwiseARModel:
         if n_chunks == 0:
             return torch.zeros(B, 0, cfg.motion_dim, device=self._device)
         self._handle()
-        audio = self._dev(audio)
         pad = n_chunks * cfg.chunk_samples - S
-        if pad:
-            audio = torch.cat([audio, audio.new_zeros(B, pad)], dim=-1)
+        audio_ready = None
+        if audio.device.type == "cpu" and audio.is_pinned():
+            # host input: the audio upload runs on a copy stream while the style encoder (which needs only the 21 KB style
+            # clips) runs on the caller's stream; wav2vec waits for the event
+            main = torch.cuda.current_stream(self._device)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self._device)
+            self._copy_stream.wait_stream(main)
+            with torch.cuda.stream(self._copy_stream):
+                audio = audio.to(self._device, torch.float32, non_blocking=True).contiguous()
+                if pad:
+                    audio = torch.cat([audio, audio.new_zeros(B, pad)], dim=-1)
+                audio_ready = torch.cuda.Event()
+                audio_ready.record(self._copy_stream)
+            audio.record_stream(main)
+        else:
+            audio = self._dev(audio)
+            if pad:
+                audio = torch.cat([audio, audio.new_zeros(B, pad)], dim=-1)
         if style_motion is not None:
             style_motion = self._dev(style_motion)
         motion = torch.empty(B, n_chunks, T, cfg.motion_dim, device=self._device)
@@ -293,7 +313,7 @@ class BitwiseARModel:
                          enc_out=torch.empty(B, n_chunks, T, cfg.code_dim, device=self._device))
         n_lanes = min(self.lanes, max(1, B // max(1, self.min_lane_clips)))
         if n_lanes <= 1:
-            self._run_clips(audio, style_motion, motion, 0, B, 0, trace, teacher_words, teacher_prev_words)
+            self._run_clips(audio, style_motion, motion, 0, B, 0, trace, teacher_words, teacher_prev_words, audio_ready)
         else:
             self.initial_words(1)                       # cached before the lanes fork
             main = torch.cuda.current_stream(self._device)
@@ -305,7 +325,7 @@ class BitwiseARModel:
                 s.wait_event(fork)
                 with torch.cuda.stream(s):
                     self._run_clips(audio, style_motion, motion, bounds[lane], bounds[lane + 1], lane, trace, teacher_words,
-                                    teacher_prev_words)
+                                    teacher_prev_words, audio_ready)
                     for t in (audio, motion, style_motion) + (tuple(trace.values()) if trace is not None else ()):
                         if isinstance(t, torch.Tensor):
                             t.record_stream(s)

@@ -245,6 +245,20 @@ def test_batched_equals_per_clip_loop(precision):
         assert torch.equal(both[b:b + 1], one)                     # same kernels, same per-row arithmetic
 
 
+def test_pinned_host_audio_equals_device_audio():
+    """Pinned host buffers go straight into the public call: the audio upload runs on a copy stream under the style encoder.
+    Same result as device-resident inputs, also when called back to back (allocator / stream ordering)."""
+    case = CASES["tiny_ragged"] if "tiny_ragged" in CASES else CASES["tiny_style"]
+    m = model("TINY", "bf16")
+    a, s = case.audio(), case.style()
+    ref = m.inference({"audio": a.to(DEV), "style_motion": None if s is None else s.to(DEV)})
+    ah = a.pin_memory()
+    sh = None if s is None else s.pin_memory()
+    for _ in range(3):
+        got = m.inference({"audio": ah, "style_motion": sh})
+        assert torch.equal(ref, got)
+
+
 def test_clip_subbatching_and_empty():
     case = CASES["tiny_style"]
     m = model("TINY", "fp32")
