@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const SkParams 
   sk_tile<TN, NST, true>(p, (int)blockIdx.x * TN, (int)blockIdx.y * SK_BM, sk_smem_dyn);
 }
 
-int g_skinny_max_m = 2048;      // option "skinny_max_m": row cap of the skinny kernel (0 = off); GemmArgs::skinny opts a call in
+int g_skinny_max_m = 512;       // option "skinny_max_m": row cap of the skinny kernel (0 = off); GemmArgs::skinny opts a call in
 int g_sk_num_sms = 0;
 
 template <int TN, int NST>
