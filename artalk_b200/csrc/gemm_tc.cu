@@ -33,6 +33,7 @@ struct TcParams {
   // `tail_bn` columns each, so the ragged wave costs tail_bn/BN of a full one (total_tiles counts the slices)
   int main_tiles, tail_split, tail_bn;
   int band_n;              // pair kernel: > 0 = N tiles per L2 band (see decode)
+  int tma_out;             // pair kernel: fp32 output chunks leave by TMA store from the warp's scratch (plain [M, N] out32 only)
   int tma_resid;           // pair kernel, EPI 1: the fp32 residual tile arrives by TMA (plain [M, N] residual, N % 32 == 0)
   int num_kb;              // K blocks of 64
   int tap_mode, tap_pad;   // tap mode: k-block j reads rows shifted by (j - tap_pad), columns of group g
@@ -103,6 +104,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -168,7 +177,9 @@ constexpr int EPI_SCRATCH_BYTES = 8 * 4096;       // 8 epilogue warps x (32 rows
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, bool row_ok, int64_t c_off, int64_t g_off, int64_t r_off,
                                           const float* bias, int col0, bool gate_bf, float4* scr, int lane,
-                                          const float4* rsm = nullptr) {
+                                          const float4* rsm = nullptr, const CUtensorMap* tmo = nullptr, int row0 = 0) {
+    // tmo: fp32 output tensor map (box 32 x 32, 128-byte swizzle = the scratch layout); the warp's chunk then leaves as one
+    // TMA store of its scratch (rows past M are clipped by the map) instead of 8 read-back + st.global rounds per thread
     // rsm: this thread's residual row of the chunk in shared memory (128 B, TMA 128-byte swizzle), or null
     const bool live = row_ok && col0 < p.N;
     const bool full = p.vec_ok && (col0 + 32 <= p.N);            // warp-uniform
@@ -265,8 +276,18 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
         }
       }
       // ---- outputs through the transposition: own row in, row-major 16-byte pieces out
+      if (tmo) {                                                   // the previous chunk's store has read the scratch
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) scr[lane * 8 + (ch ^ sw)] = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+      if (tmo) {
+        fence_proxy_async();                                       // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) tma_store_3d(tmo, smem_u32(scr), col0, row0, 0);
+        return;
+      }
       __syncwarp();
       const bool act_f32 = p.out_act && p.out_act_dt == DT_F32, act_bf = p.out_act && p.out_act_dt != DT_F32;
       if (p.out32 || act_f32) {
@@ -561,7 +582,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 constexpr int STAGES2 = 6;                                     // EPI 1 runs 5 stages: 32 KB become two residual-chunk buffers
 constexpr int RBUF_BYTES = 128 * 128;                          // 128 rows x 32 fp32
 constexpr int STAGE2_BYTES = 2 * A_STAGE_BYTES;                 // per CTA: A 128x64 + W 128x64 (bf16)
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + 8 * 4096;      // + per-warp epilogue scratch
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 1024 + 8 * 4096;     // + barriers, per-warp epilogue scratch (1024-aligned: TMA store source)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -609,7 +630,8 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+                const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmR,
+                const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   constexpr int BN = 256;
   constexpr int NST = EPI == 1 ? STAGES2 - 1 : STAGES2;
   extern __shared__ uint8_t smem_raw[];
@@ -749,7 +771,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== epilogue (both CTAs, 128 rows each) =====================
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
-    float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)) + (warp - 4) * 4096);
+    float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 1024u - smem_u32(smem_raw)) + (warp - 4) * 4096);
+    const CUtensorMap* tmo = p.tma_out ? &tmO : nullptr;
     int it = 0;
     uint32_t r_use = 0;
     pdl_wait();
@@ -782,7 +805,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           rsm = reinterpret_cast<const float4*>(smem_raw + (rbuf_base - smem_u32(smem_raw)) + half * RBUF_BYTES + (q * 32 + lane) * 128);
         }
         epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, p.bias,
-                       col_base + c * 32, gate_bf, scr, lane, rsm);
+                       col_base + c * 32, gate_bf, scr, lane, rsm, tmo, b * p.rpb + mt * 256 + (int)rank * 128 + q * 32);
         if (EPI == 1 && p.tma_resid) {             // the row was copied to registers at the top of epi_chunk
           __syncwarp();
           if (lane == 0) mbar_arrive(rempty_bar(half));
@@ -793,6 +816,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
     }
+    if (tmo && lane == 0) tma_store_wait_all();          // every bulk store of this warp has landed before the CTA exits
   }
   // ---- teardown: the peer's shared memory and the leader's barriers stay alive until both CTAs are done
   tc_fence_before();
@@ -868,8 +892,8 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
 }
 
 template <int EPI>
-int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmR, const TcParams& p,
-                    cudaStream_t st) {
+int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmR,
+                    const CUtensorMap& tmO, const TcParams& p, cudaStream_t st) {
   static int max_clusters = -1;
   if (max_clusters < 0) {
     AT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -892,12 +916,13 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_on() ? 2 : 1;
-  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, tmWt, tmR, p));
+  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, tmWt, tmR, tmO, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
 int g_pair_mode = 1;      // 0: never use the CTA-pair kernel (developer switch, ARTALK_GEMM_PAIR=0)
 int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
+int g_tma_out = 1;        // developer switch (option "gemm_tma_out")
 int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
@@ -907,6 +932,7 @@ void set_gemm_pair_mode(int on) { g_pair_mode = on; }
 void set_gemm_force_bn(int bn) { g_force_bn = bn; }
 void set_gemm_tma_resid(int on) { g_tma_resid = on; }
 void set_gemm_band_mb(int mb) { g_band_mb = mb; }
+void set_gemm_tma_out(int on) { g_tma_out = on; }
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AT_OK;
@@ -926,7 +952,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     AT_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   TcParams p;
-  p.tma_resid = 0; p.band_n = 0;
+  p.tma_resid = 0; p.band_n = 0; p.tma_out = 0;
   p.N = g.N;
   const bool batched = g.a_map.rpb > 0;
   p.rpb = batched ? g.a_map.rpb : g.M;
@@ -982,8 +1008,16 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
       if (p.tma_resid)
         AT_TRY(make_map_3d(&tmR, g.resid, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.resid_map.rs * 4, (uint64_t)g.M * g.resid_map.rs * 4,
                            32, 128, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
-      if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, tmW2t, tmR, p, st);
-      return launch_pair_epi<0>(tmA2, tmW2, tmW2t, tmR, p, st);
+      // fp32 output by TMA store: plain [M, N] out32 only (no second output), whole 32-column chunks, 16-byte aligned rows;
+      // not for batched A views (a tile's rows past the batch would land in the next batch's rows: the map only clips at M)
+      CUtensorMap tmO = tmW2;
+      p.tma_out = (g_tma_out && g.out32 && !g.out_act && p.vec_ok && !batched && g.c_map.rpb <= 0 && g.N % 32 == 0 && g.c_map.rs % 4 == 0 &&
+                   ((uintptr_t)g.out32 % 16 == 0)) ? 1 : 0;
+      if (p.tma_out)
+        AT_TRY(make_map_3d(&tmO, g.out32, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.c_map.rs * 4, (uint64_t)g.M * g.c_map.rs * 4, 32, 32,
+                           CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
+      if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
+      return launch_pair_epi<0>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
     }
   }
   // N-tile choice: persistent CTAs on 148 SMs quantise badly for the recurrence's GEMMs (e.g. 50 x 3 tiles of 128x256 =

@@ -96,6 +96,37 @@ def test_gemm_cta_pair_kernel(M, N, K, act, resid, gated):
         assert (out.float() - ref).abs().max().item() < (tol + 8e-3) * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K,resid", [(9700, 2048, 512, True), (9700, 2048, 512, False), (18944, 1280, 192, True),
+                                          (38000, 1024, 1024, True)])
+def test_gemm_cta_pair_kernel_tma_store(M, N, K, resid):
+    """fp32-only outputs of the CTA-pair kernel leave as TMA stores of each warp's 32 x 32 scratch tile (option gemm_tma_out):
+    in-place residual update and plain output, ragged last M tile (rows past M clipped by the tensor map), sliced ragged wave;
+    identical to the st.global epilogue bit for bit."""
+    dt, tol = torch.bfloat16, 3e-2
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N)
+    A = torch.randn(M, K, generator=g).to(dev(), dt)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev(), dt)
+    b = torch.randn(N, generator=g).to(dev())
+    x0 = torch.randn(M + 7, N, generator=g).to(dev())             # 7 guard rows after the matrix
+    ref = (A.double() @ W.double().t() + b.double()).float()
+    outs = []
+    for on in (1, 0):
+        _lib.check(_lib.lib().artalk_set_option(b"gemm_tma_out", on))
+        try:
+            x = x0.clone()
+            if resid:
+                run_gemm(1, A, W, M, N, K, bias=b, resid=x, out32=x)
+            else:
+                run_gemm(1, A, W, M, N, K, bias=b, out32=x)
+        finally:
+            _lib.check(_lib.lib().artalk_set_option(b"gemm_tma_out", 1))
+        assert torch.equal(x[M:], x0[M:])                           # nothing written past row M
+        outs.append(x[:M].clone())
+    want = (x0[:M] + ref) if resid else ref
+    assert (outs[0] - want).abs().max().item() < tol * max(1.0, want.abs().max().item())
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("M,N,K", [(9700, 2048, 512), (18944, 1280, 1024), (9472, 2304, 256)])
 def test_gemm_cta_pair_kernel_l2_bands(M, N, K):
     """Weights larger than L2 (the hoisted AdaLN GEMM, 116 MB) are walked in N bands so that a band of W stays L2-resident.
