@@ -134,6 +134,8 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"pdl_w2v_max_chunks", int(os.environ["ARTALK_PDL_W2V_MAX_CHUNKS"]))
         if os.environ.get("ARTALK_GEMM_TMA_RESID"):
             l.artalk_set_option(b"gemm_tma_resid", int(os.environ["ARTALK_GEMM_TMA_RESID"]))
+        if os.environ.get("ARTALK_GEMM_RESID_DEEP"):
+            l.artalk_set_option(b"gemm_resid_deep", int(os.environ["ARTALK_GEMM_RESID_DEEP"]))
         if os.environ.get("ARTALK_GEMM_TMA_OUT"):
             l.artalk_set_option(b"gemm_tma_out", int(os.environ["ARTALK_GEMM_TMA_OUT"]))
         if os.environ.get("ARTALK_GEMM_BAND_MB"):

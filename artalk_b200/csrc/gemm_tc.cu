@@ -627,19 +627,22 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int EPI>
+// RB (EPI 1): residual-chunk buffers per epilogue half. RB = 2 trades one operand stage for two more 16 KB buffers so that two
+// residual TMA loads per half are in flight: for K <= 2048 (the wav2vec out-projection: 16 k-blocks per tile) the epilogue,
+// not the MMA ring, is the critical path and each chunk exposed most of a DRAM round trip (~3 us per 32-column chunk).
+template <int EPI, int RB = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   constexpr int BN = 256;
-  constexpr int NST = EPI == 1 ? STAGES2 - 1 : STAGES2;
+  constexpr int NST = EPI == 1 ? STAGES2 - RB : STAGES2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t rbuf_base = smem_base + NST * STAGE2_BYTES;                       // EPI 1: 2 x RBUF_BYTES (1024-aligned)
-  const uint32_t bar_base = rbuf_base + (EPI == 1 ? 2 * RBUF_BYTES : 0);
-  auto rfull_bar = [&](int h) { return bar_base + 8u * (2 * STAGES2 + 5 + h); };
-  auto rempty_bar = [&](int h) { return bar_base + 8u * (2 * STAGES2 + 7 + h); };
+  const uint32_t rbuf_base = smem_base + NST * STAGE2_BYTES;                       // EPI 1: 2 * RB x RBUF_BYTES (1024-aligned)
+  const uint32_t bar_base = rbuf_base + (EPI == 1 ? 2 * RB * RBUF_BYTES : 0);
+  auto rfull_bar = [&](int i) { return bar_base + 8u * (2 * STAGES2 + 5 + i); };   // buffer i = half + 2 * slot, i < 6
+  auto rempty_bar = [&](int i) { return bar_base + 8u * (2 * STAGES2 + 11 + i); };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES2 + a); };
@@ -656,7 +659,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
-    for (int h = 0; h < 2; ++h) { mbar_init(rfull_bar(h), 1); mbar_init(rempty_bar(h), 4); }
+    for (int i = 0; i < 6; ++i) { mbar_init(rfull_bar(i), 1); mbar_init(rempty_bar(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -760,9 +763,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int row0 = b * p.rpb + mt * 256 + (int)rank * 128;
         for (int c = 0; c < (bn >> 5); ++c) {
           const int h = c & 1;
-          mbar_wait(rempty_bar(h), (use[h] & 1u) ^ 1u, p.err_flag, 0x25);
-          mbar_arrive_expect_tx(rfull_bar(h), (uint32_t)RBUF_BYTES);
-          tma_load_3d(rbuf_base + h * RBUF_BYTES, &tmR, rfull_bar(h), col_base + c * 32, row0, 0);
+          const int idx = h + 2 * (int)(use[h] % RB);
+          const uint32_t round = use[h] / RB;
+          mbar_wait(rempty_bar(idx), (round & 1u) ^ 1u, p.err_flag, 0x25);
+          mbar_arrive_expect_tx(rfull_bar(idx), (uint32_t)RBUF_BYTES);
+          tma_load_3d(rbuf_base + idx * RBUF_BYTES, &tmR, rfull_bar(idx), col_base + c * 32, row0, 0);
           ++use[h];
         }
       }
@@ -800,15 +805,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += 2) {
         const float4* rsm = nullptr;
+        const int ridx = half + 2 * (int)(r_use % RB);
         if (EPI == 1 && p.tma_resid) {
-          mbar_wait(rfull_bar(half), r_use & 1u, p.err_flag, 0x26);
-          rsm = reinterpret_cast<const float4*>(smem_raw + (rbuf_base - smem_u32(smem_raw)) + half * RBUF_BYTES + (q * 32 + lane) * 128);
+          mbar_wait(rfull_bar(ridx), (r_use / RB) & 1u, p.err_flag, 0x26);
+          rsm = reinterpret_cast<const float4*>(smem_raw + (rbuf_base - smem_u32(smem_raw)) + ridx * RBUF_BYTES + (q * 32 + lane) * 128);
         }
         epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, p.bias,
                        col_base + c * 32, gate_bf, scr, lane, rsm, tmo, b * p.rpb + mt * 256 + (int)rank * 128 + q * 32);
         if (EPI == 1 && p.tma_resid) {             // the row was copied to registers at the top of epi_chunk
           __syncwarp();
-          if (lane == 0) mbar_arrive(rempty_bar(half));
+          if (lane == 0) mbar_arrive(rempty_bar(ridx));
           ++r_use;
         }
       }
@@ -891,19 +897,19 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
   return launch_bn_epi<BN, 0>(tmA, tmW, tmWt, p, st);
 }
 
-template <int EPI>
+template <int EPI, int RB = 1>
 int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmR,
                     const CUtensorMap& tmO, const TcParams& p, cudaStream_t st) {
   static int max_clusters = -1;
   if (max_clusters < 0) {
-    AT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    AT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     cudaLaunchConfig_t qc = {};
     qc.gridDim = dim3(g_num_sms & ~1); qc.blockDim = dim3(384); qc.dynamicSmemBytes = SMEM2_BYTES;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.attrs = qa; qc.numAttrs = 1;
     int n = 0;
-    AT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<EPI>, &qc));
+    AT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<EPI, RB>, &qc));
     max_clusters = n > 0 ? n : 1;
     if (getenv("ARTALK_DEBUG")) fprintf(stderr, "[artalk] gemm pair kernel EPI=%d: max active clusters %d (SMs %d)\n", EPI, n, g_num_sms);
     if (max_clusters > g_num_sms / 2) max_clusters = g_num_sms / 2;
@@ -916,13 +922,14 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_on() ? 2 : 1;
-  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI>, tmA, tmW, tmWt, tmR, tmO, p));
+  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI, RB>, tmA, tmW, tmWt, tmR, tmO, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
 int g_pair_mode = 1;      // 0: never use the CTA-pair kernel (developer switch, ARTALK_GEMM_PAIR=0)
 int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
 int g_tma_out = 1;        // developer switch (option "gemm_tma_out")
+int g_resid_deep = 1;     // option "gemm_resid_deep": residual buffers per epilogue half beyond one: 1 -> two for K <= 2048, 2 -> also three for K <= 1024
 int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
@@ -933,6 +940,7 @@ void set_gemm_force_bn(int bn) { g_force_bn = bn; }
 void set_gemm_tma_resid(int on) { g_tma_resid = on; }
 void set_gemm_band_mb(int mb) { g_band_mb = mb; }
 void set_gemm_tma_out(int on) { g_tma_out = on; }
+void set_gemm_resid_deep(int on) { g_resid_deep = on; }
 
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return AT_OK;
@@ -1016,6 +1024,8 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
       if (p.tma_out)
         AT_TRY(make_map_3d(&tmO, g.out32, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.c_map.rs * 4, (uint64_t)g.M * g.c_map.rs * 4, 32, 32,
                            CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
+      if (p.tma_resid && g_resid_deep >= 2 && p.num_kb <= 16) return launch_pair_epi<1, 3>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
+      if (p.tma_resid && g_resid_deep >= 1 && p.num_kb <= 32) return launch_pair_epi<1, 2>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       return launch_pair_epi<0>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
     }
