@@ -280,6 +280,25 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
       }
+      if (tmo && p.tma_out == 2) {
+        // bf16 output tile (32 rows x 64 B, 64-byte swizzle: 16-byte piece j of row r sits at j ^ ((r >> 1) & 3)): packed in
+        // registers, 4 conflict-free 16-byte shared stores per thread, one TMA store per warp
+        uint4* s16 = reinterpret_cast<uint4*>(scr);
+        const int sw4 = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          s16[lane * 4 + (j ^ sw4)] = pk;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma_store_3d(tmo, smem_u32(scr), col0, row0, 0);
+        return;
+      }
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) scr[lane * 8 + (ch ^ sw)] = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
       if (tmo) {
@@ -851,7 +870,8 @@ EncodeTiledFn get_encode() {
 }
 
 int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes,
-                uint32_t b0, uint32_t b1, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+                uint32_t b0, uint32_t b1, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   AT_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -859,7 +879,7 @@ int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, dtype, 3, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u) base=%p", (int)r,
@@ -928,7 +948,7 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
 }
 int g_pair_mode = 1;      // 0: never use the CTA-pair kernel (developer switch, ARTALK_GEMM_PAIR=0)
 int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
-int g_tma_out = 1;        // developer switch (option "gemm_tma_out")
+int g_tma_out = 2;        // option "gemm_tma_out": 0 = st.global epilogue, 1 = TMA stores for fp32-only outputs, 2 = also bf16-only outputs
 int g_resid_deep = 1;     // option "gemm_resid_deep": residual buffers per epilogue half beyond one: 1 -> two for K <= 2048, 2 -> also three for K <= 1024
 int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
@@ -1024,6 +1044,13 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
       if (p.tma_out)
         AT_TRY(make_map_3d(&tmO, g.out32, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.c_map.rs * 4, (uint64_t)g.M * g.c_map.rs * 4, 32, 32,
                            CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
+      // bf16-only output: same, 32 x 32 bf16 tiles with the 64-byte swizzle
+      else if (g_tma_out >= 2 && !g.out32 && g.out_act && g.out_act_dt == DT_BF16 && p.vec_ok && !batched && g.c_map.rpb <= 0 &&
+               g.N % 32 == 0 && g.c_map.rs % 8 == 0 && ((uintptr_t)g.out_act % 16 == 0)) {
+        p.tma_out = 2;
+        AT_TRY(make_map_3d(&tmO, g.out_act, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.c_map.rs * 2, (uint64_t)g.M * g.c_map.rs * 2, 32, 32,
+                           CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B));
+      }
       if (p.tma_resid && g_resid_deep >= 2 && p.num_kb <= 16) return launch_pair_epi<1, 3>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (p.tma_resid && g_resid_deep >= 1 && p.num_kb <= 32) return launch_pair_epi<1, 2>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);

@@ -110,7 +110,8 @@ def test_gemm_cta_pair_kernel_tma_store(M, N, K, resid):
     x0 = torch.randn(M + 7, N, generator=g).to(dev())             # 7 guard rows after the matrix
     ref = (A.double() @ W.double().t() + b.double()).float()
     outs = []
-    for on in (1, 0):
+    bouts = []
+    for on in (2, 0):
         _lib.check(_lib.lib().artalk_set_option(b"gemm_tma_out", on))
         try:
             x = x0.clone()
@@ -118,13 +119,18 @@ def test_gemm_cta_pair_kernel_tma_store(M, N, K, resid):
                 run_gemm(1, A, W, M, N, K, bias=b, resid=x, out32=x)
             else:
                 run_gemm(1, A, W, M, N, K, bias=b, out32=x)
+            xb = torch.full((M + 7, N), 7.0, device=dev(), dtype=dt)   # bf16-only output (64-byte-swizzle tiles), GELU epilogue
+            run_gemm(1, A, W, M, N, K, bias=b, act=1, out_act=xb)
         finally:
-            _lib.check(_lib.lib().artalk_set_option(b"gemm_tma_out", 1))
-        assert torch.equal(x[M:], x0[M:])                           # nothing written past row M
-        outs.append(x[:M].clone())
+            _lib.check(_lib.lib().artalk_set_option(b"gemm_tma_out", 2))
+        assert torch.equal(x[M:], x0[M:]) and bool((xb[M:] == 7.0).all())      # nothing written past row M
+        outs.append(x[:M].clone()); bouts.append(xb[:M].clone())
     want = (x0[:M] + ref) if resid else ref
     assert (outs[0] - want).abs().max().item() < tol * max(1.0, want.abs().max().item())
     assert torch.equal(outs[0], outs[1])
+    gref = F.gelu(ref.double()).float()
+    assert (bouts[0].float() - gref).abs().max().item() < (tol + 8e-3) * max(1.0, gref.abs().max().item())
+    assert torch.equal(bouts[0], bouts[1])
 
 
 @pytest.mark.parametrize("M,N,K", [(9700, 2048, 512), (18944, 1280, 1024), (9472, 2304, 256)])
