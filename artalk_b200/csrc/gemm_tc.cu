@@ -161,7 +161,7 @@ template <int BN> struct TileCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 4096 /*epilogue scratch*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + 8 * 4096 /*epilogue scratch, 1024-aligned: TMA store source*/;
 };
 
 // One 32-column chunk of 32 output rows (one warp; thread = row, as tcgen05.ld delivers the accumulator):
@@ -177,7 +177,8 @@ constexpr int EPI_SCRATCH_BYTES = 8 * 4096;       // 8 epilogue warps x (32 rows
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, bool row_ok, int64_t c_off, int64_t g_off, int64_t r_off,
                                           const float* bias, int col0, bool gate_bf, float4* scr, int lane,
-                                          const float4* rsm = nullptr, const CUtensorMap* tmo = nullptr, int row0 = 0) {
+                                          const float4* rsm = nullptr, const CUtensorMap* tmo = nullptr, int row0 = 0, int bz = 0) {
+    // (row0, bz): first row of the warp's 32 inside its batch, batch index (output map = (cols, rows per batch, batches))
     // tmo: fp32 output tensor map (box 32 x 32, 128-byte swizzle = the scratch layout); the warp's chunk then leaves as one
     // TMA store of its scratch (rows past M are clipped by the map) instead of 8 read-back + st.global rounds per thread
     // rsm: this thread's residual row of the chunk in shared memory (128 B, TMA 128-byte swizzle), or null
@@ -296,7 +297,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tma_store_3d(tmo, smem_u32(scr), col0, row0, 0);
+        if (lane == 0) tma_store_3d(tmo, smem_u32(scr), col0, row0, bz);
         return;
       }
 #pragma unroll
@@ -304,7 +305,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
       if (tmo) {
         fence_proxy_async();                                       // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
-        if (lane == 0) tma_store_3d(tmo, smem_u32(scr), col0, row0, 0);
+        if (lane == 0) tma_store_3d(tmo, smem_u32(scr), col0, row0, bz);
         return;
       }
       __syncwarp();
@@ -362,7 +363,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
 template <int BN, int EPI>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmWt, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -484,7 +485,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // and always miss), and the chunk's loads are issued ahead of the tcgen05.ld so both latencies overlap.
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
-    float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)) + (warp - 4) * 4096);
+    float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 1024u - smem_u32(smem_raw)) + (warp - 4) * 4096);
+    const CUtensorMap* tmo = (EPI != 2 && p.tma_out) ? &tmO : nullptr;
     int it = 0;
     pdl_wait();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -574,12 +576,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += 2)
         epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, bias,
-                       col_base + c * 32, gate_bf, scr, lane);
+                       col_base + c * 32, gate_bf, scr, lane, nullptr, tmo, mt * BM + q * 32, b);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
+    if (tmo && lane == 0) tma_store_wait_all();          // every bulk store of this warp has landed before the CTA exits
   }
   // ---- teardown
   tc_fence_before();
@@ -830,7 +833,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           rsm = reinterpret_cast<const float4*>(smem_raw + (rbuf_base - smem_u32(smem_raw)) + ridx * RBUF_BYTES + (q * 32 + lane) * 128);
         }
         epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, p.bias,
-                       col_base + c * 32, gate_bf, scr, lane, rsm, tmo, b * p.rpb + mt * 256 + (int)rank * 128 + q * 32);
+                       col_base + c * 32, gate_bf, scr, lane, rsm, tmo, mt * 256 + (int)rank * 128 + q * 32, b);
         if (EPI == 1 && p.tma_resid) {             // the row was copied to registers at the top of epi_chunk
           __syncwarp();
           if (lane == 0) mbar_arrive(rempty_bar(ridx));
@@ -892,9 +895,29 @@ int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint
 
 unsigned int* g_err_flag = nullptr;
 int g_num_sms = 0;
+extern int g_tma_out;
+
+// Output tensor map for the TMA-store epilogue: (cols, rows per batch, batches), 32 x 32 boxes, so rows a tile computes past
+// its batch (or past M) are clipped. fp32-only outputs (128-byte swizzle = the scratch layout) or bf16-only outputs (64-byte
+// swizzle); plain output rows, whole 32-column chunks, no groups. Returns 0 (st.global epilogue), 1 (fp32) or 2 (bf16).
+int make_out_map(CUtensorMap* tmO, const GemmArgs& g, int rpb, int n_batches, bool vec_ok) {
+  if (!g_tma_out || !vec_ok || g.c_map.rpb > 0 || g.N % 32 != 0 || g.groups != 1 || g.qkv_mode) return 0;
+  if (g.out32 && !g.out_act && g.c_map.rs % 4 == 0 && ((uintptr_t)g.out32 % 16 == 0)) {
+    if (make_map_3d(tmO, g.out32, (uint64_t)g.N, (uint64_t)rpb, (uint64_t)n_batches, (uint64_t)g.c_map.rs * 4,
+                    (uint64_t)rpb * g.c_map.rs * 4, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32) != AT_OK) return -1;
+    return 1;
+  }
+  if (g_tma_out >= 2 && !g.out32 && g.out_act && g.out_act_dt == DT_BF16 && g.c_map.rs % 8 == 0 && ((uintptr_t)g.out_act % 16 == 0)) {
+    if (make_map_3d(tmO, g.out_act, (uint64_t)g.N, (uint64_t)rpb, (uint64_t)n_batches, (uint64_t)g.c_map.rs * 2,
+                    (uint64_t)rpb * g.c_map.rs * 2, 32, 32, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B) != AT_OK) return -1;
+    return 2;
+  }
+  return 0;
+}
 
 template <int BN, int EPI>
-int launch_bn_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const TcParams& p, cudaStream_t st) {
+int launch_bn_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmO, const TcParams& p,
+                  cudaStream_t st) {
   using Cfg = TileCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -903,18 +926,19 @@ int launch_bn_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensor
   }
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   g_trace_dims[0] = p.rpb * p.n_batches; g_trace_dims[1] = p.N; g_trace_dims[2] = p.num_kb * BK * p.groups;
-  AT_CUDA(launch_k(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, tmA, tmW, tmWt, p));
+  AT_CUDA(launch_k(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, tmA, tmW, tmWt, tmO, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
 
 template <int BN>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const TcParams& p, cudaStream_t st) {
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmO, const TcParams& p,
+              cudaStream_t st) {
   if constexpr (BN >= 128) {
-    if (p.qkv_mode) return launch_bn_epi<BN, 2>(tmA, tmW, tmWt, p, st);
+    if (p.qkv_mode) return launch_bn_epi<BN, 2>(tmA, tmW, tmWt, tmO, p, st);
   }
-  if (p.gate || p.resid) return launch_bn_epi<BN, 1>(tmA, tmW, tmWt, p, st);
-  return launch_bn_epi<BN, 0>(tmA, tmW, tmWt, p, st);
+  if (p.gate || p.resid) return launch_bn_epi<BN, 1>(tmA, tmW, tmWt, tmO, p, st);
+  return launch_bn_epi<BN, 0>(tmA, tmW, tmWt, tmO, p, st);
 }
 
 template <int EPI, int RB = 1>
@@ -948,7 +972,7 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
 }
 int g_pair_mode = 1;      // 0: never use the CTA-pair kernel (developer switch, ARTALK_GEMM_PAIR=0)
 int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
-int g_tma_out = 2;        // option "gemm_tma_out": 0 = st.global epilogue, 1 = TMA stores for fp32-only outputs, 2 = also bf16-only outputs
+int g_tma_out = 2;        // (declared above make_out_map) option "gemm_tma_out": 0 = st.global epilogue, 1 = TMA stores for fp32-only outputs, 2 = also bf16-only outputs
 int g_resid_deep = 1;     // option "gemm_resid_deep": residual buffers per epilogue half beyond one: 1 -> two for K <= 2048, 2 -> also three for K <= 1024
 int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
@@ -1036,20 +1060,11 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
       if (p.tma_resid)
         AT_TRY(make_map_3d(&tmR, g.resid, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.resid_map.rs * 4, (uint64_t)g.M * g.resid_map.rs * 4,
                            32, 128, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
-      // fp32 output by TMA store: plain [M, N] out32 only (no second output), whole 32-column chunks, 16-byte aligned rows;
-      // not for batched A views (a tile's rows past the batch would land in the next batch's rows: the map only clips at M)
       CUtensorMap tmO = tmW2;
-      p.tma_out = (g_tma_out && g.out32 && !g.out_act && p.vec_ok && !batched && g.c_map.rpb <= 0 && g.N % 32 == 0 && g.c_map.rs % 4 == 0 &&
-                   ((uintptr_t)g.out32 % 16 == 0)) ? 1 : 0;
-      if (p.tma_out)
-        AT_TRY(make_map_3d(&tmO, g.out32, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.c_map.rs * 4, (uint64_t)g.M * g.c_map.rs * 4, 32, 32,
-                           CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
-      // bf16-only output: same, 32 x 32 bf16 tiles with the 64-byte swizzle
-      else if (g_tma_out >= 2 && !g.out32 && g.out_act && g.out_act_dt == DT_BF16 && p.vec_ok && !batched && g.c_map.rpb <= 0 &&
-               g.N % 32 == 0 && g.c_map.rs % 8 == 0 && ((uintptr_t)g.out_act % 16 == 0)) {
-        p.tma_out = 2;
-        AT_TRY(make_map_3d(&tmO, g.out_act, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.c_map.rs * 2, (uint64_t)g.M * g.c_map.rs * 2, 32, 32,
-                           CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B));
+      {
+        const int t = make_out_map(&tmO, g, p.rpb, p.n_batches, p.vec_ok != 0);
+        if (t < 0) return AT_ECUDA;
+        p.tma_out = t;
       }
       if (p.tma_resid && g_resid_deep >= 2 && p.num_kb <= 16) return launch_pair_epi<1, 3>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (p.tma_resid && g_resid_deep >= 1 && p.num_kb <= 32) return launch_pair_epi<1, 2>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
@@ -1130,11 +1145,17 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   CUtensorMap tmWt = tmW;
   if (p.tail_split > 1)
     AT_TRY(make_map_3d(&tmWt, g.W, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.groups, (uint64_t)g.ldw * 2, w_s2, BK, (uint32_t)p.tail_bn));
+  CUtensorMap tmO = tmW;
+  if (!p.tap_mode) {
+    const int t = make_out_map(&tmO, g, p.rpb, p.n_batches, p.vec_ok != 0);
+    if (t < 0) return AT_ECUDA;
+    p.tma_out = t;
+  }
   switch (BN) {
-    case 256: return launch_bn<256>(tmA, tmW, tmWt, p, st);
-    case 128: return launch_bn<128>(tmA, tmW, tmWt, p, st);
-    case 64: return launch_bn<64>(tmA, tmW, tmWt, p, st);
-    default: return launch_bn<32>(tmA, tmW, tmWt, p, st);
+    case 256: return launch_bn<256>(tmA, tmW, tmWt, tmO, p, st);
+    case 128: return launch_bn<128>(tmA, tmW, tmWt, tmO, p, st);
+    case 64: return launch_bn<64>(tmA, tmW, tmWt, tmO, p, st);
+    default: return launch_bn<32>(tmA, tmW, tmWt, tmO, p, st);
   }
 }
 
