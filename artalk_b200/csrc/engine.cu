@@ -511,7 +511,9 @@ int Engine::vae_stack(const char* side, int n, int rows, int split, float* x, vo
     g = gemm_args();
     g.A = f; g.a_map = plain_rows(FF); g.W = getw(S("vae.%s.l%d.ff2.w", side, l)); g.ldw = FF; g.M = M; g.N = VH; g.K = FF;
     g.bias = get<float>(S("vae.%s.l%d.ff2.b", side, l)); g.resid = x; g.resid_map = plain_rows(VH); g.out32 = x; g.c_map = plain_rows(VH);
-    if (adt != DT_F32) { g.out_act = xa; g.out_act_dt = adt; }
+    // the bf16 copy of x is read by this layer's FFN1 (written by the out-projection above) and, after the last layer, by the
+    // caller's output mapping: only the last FFN2 has to write it (single-output GEMMs take the TMA-store epilogue)
+    if (adt != DT_F32 && l == c.vae_depth - 1) { g.out_act = xa; g.out_act_dt = adt; }
     AT_TRY(gemm(g, st));
   }
   return AT_OK;
@@ -531,7 +533,7 @@ int Engine::vae_decode(const uint32_t* prev_words, const uint32_t* words, int n,
   GemmArgs g = gemm_args();
   g.A = z; g.a_map = plain_rows(c.code_dim); g.W = getw("vae.dec.in.w"); g.ldw = c.code_dim; g.M = M; g.N = VH; g.K = c.code_dim;
   g.bias = get<float>("vae.dec.in.b"); g.act = ACT_LEAKY02; g.out32 = x; g.c_map = plain_rows(VH);
-  if (adt != DT_F32) { g.out_act = xa; g.out_act_dt = adt; }
+  if (adt != DT_F32 && c.vae_depth == 0) { g.out_act = xa; g.out_act_dt = adt; }   // layer 0 rewrites xa before anyone reads it
   AT_TRY(gemm(g, st));
   AT_TRY(vae_stack("dec", n, rows, T, x, xa, st));
   // out_mapping on the new half only (rows T..2T of each clip); motion_std / motion_mean folded into W, b
@@ -561,7 +563,7 @@ int Engine::vae_encode_bits(const float* motion, int n, uint32_t* words_out, flo
   GemmArgs g = gemm_args();
   g.A = xin; g.a_map = plain_rows(KP); g.W = getw("vae.enc.in.w"); g.ldw = KP; g.M = M; g.N = VH; g.K = KP;
   g.bias = get<float>("vae.enc.in.b"); g.act = ACT_LEAKY02; g.out32 = x; g.c_map = plain_rows(VH);
-  if (adt != DT_F32) { g.out_act = xa; g.out_act_dt = adt; }
+  if (adt != DT_F32 && c.vae_depth == 0) { g.out_act = xa; g.out_act_dt = adt; }
   AT_TRY(gemm(g, st));
   AT_TRY(vae_stack("enc", n, T, 0, x, xa, st));
   g = gemm_args();
