@@ -139,3 +139,25 @@ def test_word_packing_roundtrip():
     assert w.dtype == torch.int32 and int(w[0, 0]) == -1
     assert torch.equal(unpack_words(w), bits)
     assert torch.equal(gu.unpack_bits(w.numpy().view(np.uint32)), bits)
+
+
+def test_l2_band_walk_is_a_permutation_of_the_tiles():
+    """The CTA-pair GEMM walks N in L2-sized bands when the weights exceed L2 (artalk_b200/csrc/gemm_tc.cu, `decode` of
+    gemm_tc2_kernel). Host restatement of that index map: every (M tile, N tile) is visited exactly once, bands are visited in
+    order with all M tiles inside a band, and the last band may be narrower."""
+    def decode(big, m_all, n_tiles_n, band_n):
+        per_band = band_n * m_all
+        n_bands = (n_tiles_n + band_n - 1) // band_n
+        band = min(big // per_band, n_bands - 1)
+        r = big - band * per_band
+        width = n_tiles_n - band * band_n if band == n_bands - 1 else band_n
+        rest = r // width
+        return rest, band * band_n + (r - rest * width)          # (M tile, N tile)
+
+    for m_all, n_tiles_n, band_n in [(46, 222, 64), (5, 8, 4), (74, 5, 2), (3, 7, 7), (3, 7, 100), (1, 1, 1), (10, 9, 4)]:
+        seen = [decode(t, m_all, n_tiles_n, band_n) for t in range(m_all * n_tiles_n)]
+        assert sorted(seen) == [(m, n) for m in range(m_all) for n in range(n_tiles_n)]
+        bands = [n // band_n for _, n in seen]
+        assert bands == sorted(bands)                              # one band after the other
+        first_band = [mn for mn in seen if mn[1] < band_n]
+        assert len({m for m, _ in first_band}) == m_all            # every M tile inside the band
