@@ -146,6 +146,8 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"attn_simt_max_lq", int(os.environ["ARTALK_ATTN_SIMT_MAX_LQ"]))
         if os.environ.get("ARTALK_SKINNY_MAX_M"):         # 0: the latency-path kernels (skinny.cu) are never taken
             l.artalk_set_option(b"skinny_max_m", int(os.environ["ARTALK_SKINNY_MAX_M"]))
+        if os.environ.get("ARTALK_FLAME_V2"):             # opt-in packed-pair FLAME skinning epilogue (flame_tc.cu)
+            l.artalk_set_option(b"flame_v2", int(os.environ["ARTALK_FLAME_V2"]))
         if os.environ.get("ARTALK_AR_SMALL"):             # 0: the few-token scale steps run as separate kernels
             l.artalk_set_option(b"ar_small", int(os.environ["ARTALK_AR_SMALL"]))
         if os.environ.get("ARTALK_SKINNY_TOKENS"):

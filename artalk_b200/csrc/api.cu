@@ -166,6 +166,7 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "gemm_band_mb")) { set_gemm_band_mb(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_tma_resid")) { set_gemm_tma_resid(value); return AT_OK; }
   if (!std::strcmp(name, "attn_simt_max_lq")) { set_attn_simt_max_lq(value); return AT_OK; }
+  if (!std::strcmp(name, "flame_v2")) { set_flame_v2(value); return AT_OK; }
   if (!std::strcmp(name, "ar_small")) { set_ar_small(value); return AT_OK; }
   if (!std::strcmp(name, "skinny_tokens")) { g_skinny_tokens = value; return AT_OK; }
   if (!std::strcmp(name, "skinny_max_m")) { set_skinny_max_m(value); return AT_OK; }

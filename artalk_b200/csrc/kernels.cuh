@@ -170,6 +170,7 @@ struct FlameModel {
   const void* bsplit_full; int ks_full;
   const void* bsplit_expr; int ks_expr;
 };
+void set_flame_v2(int on);
 int launch_flame_tc(const FlameModel& m, const float* base, const float* coef, int coef_stride, int l_begin, int n_l,
                     const void* b_split, int KS, void* a_split_ws, float* verts, int n_frames, cudaStream_t st);
 // shape (N,300) [stride 0 allowed for a shared shape row], expr (N,100), pose6 (N,6) -> verts (N,V,3)
