@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ARTALK_LIB") or os.path.join(HERE, "lib", "libartalk_b200.so")      # ARTALK_LIB: A/B builds
 
 F32, BF16, I32 = 0, 1, 2
-PRECISION = {"fp32": 0, "bf16": 1}
+PRECISION = {"fp32": 0, "bf16": 1, "bf16x3": 2, "bf16x6": 3}
 
 
 class ArtalkError(RuntimeError):
@@ -51,6 +51,7 @@ class Gemm(C.Structure):
         ("gate", C.c_void_p), ("gate_dt", C.c_int), ("gate_map", RowMap),
         ("resid", C.c_void_p), ("resid_map", RowMap),
         ("out32", C.c_void_p), ("out_act", C.c_void_p), ("out_act_dt", C.c_int), ("c_map", RowMap),
+        ("tap_slots", C.c_int), ("exact", C.c_int),
     ]
 
 
@@ -85,6 +86,7 @@ SYMBOLS = {
     "artalk_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "artalk_enable_graphs": (C.c_int, [C.c_void_p, C.c_int]),
     "artalk_set_latency_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "artalk_graph_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "artalk_audio_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "artalk_style_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "artalk_motion_to_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -107,6 +109,7 @@ SYMBOLS = {
     "artalk_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "artalk_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "artalk_op_gemm": (C.c_int, [C.POINTER(Gemm), C.c_int, C.c_void_p]),
+    "artalk_op_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "artalk_op_attention": (C.c_int, [C.POINTER(Attn), C.c_void_p]),
     "artalk_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_float, C.c_int, C.c_void_p]),
@@ -148,12 +151,8 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"skinny_max_m", int(os.environ["ARTALK_SKINNY_MAX_M"]))
         if os.environ.get("ARTALK_FLAME_V2"):             # opt-in packed-pair FLAME skinning epilogue (flame_tc.cu)
             l.artalk_set_option(b"flame_v2", int(os.environ["ARTALK_FLAME_V2"]))
-        if os.environ.get("ARTALK_AR_SMALL"):             # 0: the few-token scale steps run as separate kernels
-            l.artalk_set_option(b"ar_small", int(os.environ["ARTALK_AR_SMALL"]))
         if os.environ.get("ARTALK_SKINNY_TOKENS"):
             l.artalk_set_option(b"skinny_tokens", int(os.environ["ARTALK_SKINNY_TOKENS"]))
-        if os.environ.get("ARTALK_ATTN_FEW_MAX_LQ"):
-            l.artalk_set_option(b"attn_few_max_lq", int(os.environ["ARTALK_ATTN_FEW_MAX_LQ"]))
         if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":
             l.artalk_set_option(b"gemm_pair", 0)
         _lib = l
@@ -164,6 +163,13 @@ def check(status: int) -> None:
     if status != 0:
         msg = lib().artalk_last_error()
         raise ArtalkError("artalk_b200 call failed (code %d): %s" % (status, msg.decode() if msg else "?"))
+
+
+def call(device, fn, *args) -> None:
+    """One C-ABI call with ``device`` current: the library allocates and launches on the current device, so an engine on
+    ``cuda:1`` must not run with device 0 current (a stream handle of another device is an invalid resource handle)."""
+    with torch.cuda.device(device):
+        check(fn(*args))
 
 
 def ptr(t) -> int:
@@ -180,6 +186,8 @@ def require_cuda(device) -> torch.device:
         raise ArtalkError("artalk_b200 runs on CUDA devices only (got %r); the product has no CPU path" % (device,))
     if not torch.cuda.is_available():
         raise ArtalkError("CUDA is not available: artalk_b200 has no CPU fallback")
+    if d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
     return d
 
 

@@ -83,8 +83,8 @@ def resample_mono(waveform: torch.Tensor, sr: int, new_sr: int = TARGET_SR, devi
         return x.mean(dim=0) if C_ > 1 else x[0].clone()
     out_len = -((-new * S) // orig)        # ceil(new * S / orig)
     out = torch.empty(out_len, device=dev, dtype=torch.float32)
-    _lib.check(_lib.lib().artalk_resample_mono(x.data_ptr(), C_, x.stride(0), S, bank.data_ptr(), orig, new, bank.shape[1], width,
-                                               out.data_ptr(), out_len, _lib.stream_ptr(dev)))
+    _lib.call(dev, _lib.lib().artalk_resample_mono, x.data_ptr(), C_, x.stride(0), S, bank.data_ptr(), orig, new, bank.shape[1], width,
+                                               out.data_ptr(), out_len, _lib.stream_ptr(dev))
     return out
 
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libartalk_b200.so")
-SOURCES = ["norms.cu", "gemm_simt.cu", "gemm_tc.cu", "skinny.cu", "attention.cu", "attention_tc.cu", "bits.cu", "flame.cu", "flame_tc.cu", "postproc.cu", "frontend.cu",
+SOURCES = ["norms.cu", "gemm_simt.cu", "gemm_tc.cu", "skinny.cu", "split.cu", "attention.cu", "attention_tc.cu", "bits.cu", "flame.cu", "flame_tc.cu", "postproc.cu", "frontend.cu",
            "engine.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -56,9 +56,11 @@ def build(verbose: bool = False, force: bool = False) -> str:
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        # static cudart (nvcc default); the driver entry point for TMA descriptors is fetched at run time with
-        # cudaGetDriverEntryPoint, so the library also loads on a box without libcuda (CPU tests)
-        cmd = [NVCC, "-shared", "-o", LIB] + objs
+        # shared cudart: torch already loads libcudart.so.12 into the process, and the shipped library then carries no copy of
+        # the runtime (the static runtime embeds entry-point names this repo never calls). The driver entry point for TMA
+        # descriptors is fetched at run time with cudaGetDriverEntryPoint, so the library also loads on a box without libcuda
+        cudart = "static" if os.environ.get("ARTALK_STATIC_CUDART") == "1" else "shared"      # developer switch
+        cmd = [NVCC, "-shared", "--cudart", cudart, "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr[-4000:])

@@ -17,7 +17,7 @@ static inline RowMap rm(const artalk_rowmap_t& m) { RowMap r; r.rpb = m.rpb; r.b
 extern "C" {
 
 const char* artalk_last_error(void) { return last_error(); }
-int artalk_abi_version(void) { return 1; }
+int artalk_abi_version(void) { return 2; }
 
 int artalk_create(const artalk_config_t* cfg, artalk_engine_t** out) {
   AT_REQUIRE(cfg && out, "artalk_create: null argument");
@@ -31,9 +31,13 @@ int artalk_create(const artalk_config_t* cfg, artalk_engine_t** out) {
 int artalk_destroy(artalk_engine_t* e) {
   if (!e) return AT_OK;
   e->eng.drop_graphs();
+  e->eng.free_split();
+  if (e->eng.split_buf) cudaFree(e->eng.split_buf);
   if (e->eng.ws) cudaFree(e->eng.ws);
-  if (e->eng.ar_table) cudaFree(e->eng.ar_table);
-  if (e->eng.ar_sync) cudaFree(e->eng.ar_sync);
+  if (e->eng.gstream) cudaStreamDestroy(e->eng.gstream);
+  if (e->eng.gev_in) cudaEventDestroy(e->eng.gev_in);
+  if (e->eng.gev_out) cudaEventDestroy(e->eng.gev_out);
+  for (auto& ev : e->eng.prof_ev) cudaEventDestroy(ev);
   delete e;
   return AT_OK;
 }
@@ -55,7 +59,21 @@ size_t artalk_workspace_bytes(const artalk_engine_t* e) { return e ? e->eng.ws_c
 int artalk_enable_graphs(artalk_engine_t* e, int enable) {
   AT_REQUIRE(e, "null engine");
   if (!enable) e->eng.drop_graphs();
+  else e->eng.graph_failure.clear();
   e->eng.use_graphs = enable != 0;
+  return AT_OK;
+}
+
+int artalk_graph_status(const artalk_engine_t* e, int* n_graphs, int* n_replays) {
+  AT_REQUIRE(e, "null engine");
+  int n = 0;
+  for (auto& kv : e->eng.graphs) n += kv.second.exec != nullptr;
+  if (n_graphs) *n_graphs = n;
+  if (n_replays) *n_replays = e->eng.graph_replays;
+  if (!e->eng.graph_failure.empty()) {
+    set_last_error("%s", e->eng.graph_failure.c_str());
+    return AT_ESTATE;
+  }
   return AT_OK;
 }
 
@@ -152,10 +170,11 @@ int artalk_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_i
   return launch_ema_scan(points, frame_stride, idx, n_idx, n_frames, state, has_state, keep, (cudaStream_t)stream);
 }
 
-unsigned long long artalk_launch_count(void) { return g_launch_count; }
-int artalk_enable_pdl(int enable) { g_pdl = enable != 0; return AT_OK; }
+unsigned long long artalk_launch_count(void) { return g_launch_count.load(); }
+int artalk_enable_pdl(int enable) { g_pdl = enable != 0; ++g_option_epoch; return AT_OK; }
 int artalk_set_option(const char* name, int value) {
   AT_REQUIRE(name, "artalk_set_option: null name");
+  ++g_option_epoch;                          // kernel selection may change: chunk graphs captured so far are re-captured
   if (!std::strcmp(name, "pdl")) { g_pdl = value != 0; return AT_OK; }
   if (!std::strcmp(name, "pdl_mask")) { g_pdl_mask = value; return AT_OK; }
   if (!std::strcmp(name, "pdl_w2v_max_chunks")) { g_pdl_w2v_max_chunks = value; return AT_OK; }
@@ -167,10 +186,8 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "gemm_tma_resid")) { set_gemm_tma_resid(value); return AT_OK; }
   if (!std::strcmp(name, "attn_simt_max_lq")) { set_attn_simt_max_lq(value); return AT_OK; }
   if (!std::strcmp(name, "flame_v2")) { set_flame_v2(value); return AT_OK; }
-  if (!std::strcmp(name, "ar_small")) { set_ar_small(value); return AT_OK; }
   if (!std::strcmp(name, "skinny_tokens")) { g_skinny_tokens = value; return AT_OK; }
   if (!std::strcmp(name, "skinny_max_m")) { set_skinny_max_m(value); return AT_OK; }
-  if (!std::strcmp(name, "attn_few_max_lq")) { set_attn_few_max_lq(value); return AT_OK; }
   set_last_error("artalk_set_option: unknown option '%s'", name);
   return AT_EINVAL;
 }
@@ -194,8 +211,13 @@ int artalk_op_gemm(const artalk_gemm_t* a, int precision, void* stream) {
   g.bias = a->bias; g.act = a->act; g.gate = a->gate; g.gate_dt = a->gate_dt; g.gate_map = rm(a->gate_map);
   g.resid = a->resid; g.resid_map = rm(a->resid_map); g.out32 = a->out32; g.out_act = a->out_act; g.out_act_dt = a->out_act_dt;
   g.c_map = rm(a->c_map);
-  g.skinny = 1;                 // op-level calls: any shape within option "skinny_max_m" may take the latency kernel
+  g.tap_slots = a->tap_slots > 0 ? a->tap_slots : 1; g.exact = a->exact;
+  g.skinny = g.exact ? 0 : 1;   // op-level calls: any shape within option "skinny_max_m" may take the latency kernel (bf16-grade epilogue)
   return precision == ARTALK_PRECISION_FP32 ? launch_gemm_simt(g, (cudaStream_t)stream) : launch_gemm_tc(g, (cudaStream_t)stream);
+}
+
+int artalk_op_split_bf16(const float* x, void* out, int64_t n, int slots, int is_w, void* stream) {
+  return launch_split_bf16(x, out, n, slots, is_w, (cudaStream_t)stream);
 }
 
 int artalk_op_attention(const artalk_attn_t* a, void* stream) {

@@ -125,7 +125,6 @@ void set_attn_simt_max_lq(int v) { g_attn_simt_max_lq = v; }
 
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
   if (a.n_seq <= 0 || a.lq <= 0) return AT_OK;
-  if (attention_few_supported(a)) return launch_attention_few(a, st);
   if (attention_tc_supported(a) && a.lq > g_attn_simt_max_lq) return launch_attention_tc(a, st);
   AT_REQUIRE(a.head_dim == 64 || a.head_dim == 32, "attention: head_dim %d", a.head_dim);
   AT_REQUIRE(a.lk > 0 && a.k_rs % 4 == 0 && a.v_rs % 4 == 0 && a.k_ss % 4 == 0 && a.v_ss % 4 == 0,

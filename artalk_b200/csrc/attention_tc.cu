@@ -368,8 +368,6 @@ int make_map(CUtensorMap* m, const void* base, uint64_t width, uint64_t rows, ui
   return make_map_bf16_3d(m, base, width, rows, seqs, rs_bytes, ss_bytes, 64, box_rows);
 }
 
-unsigned int* g_err_flag = nullptr;
-int g_num_sms = 0;
 }  // namespace
 
 bool attention_tc_supported(const AttnArgs& a) {
@@ -381,14 +379,11 @@ bool attention_tc_supported(const AttnArgs& a) {
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   if (a.n_seq <= 0 || a.lq <= 0) return AT_OK;
   AT_REQUIRE(attention_tc_supported(a), "attention_tc: unsupported shape/stride (lk=%d head_dim=%d)", a.lk, a.head_dim);
-  if (!g_err_flag) {
-    AT_CUDA(cudaMalloc((void**)&g_err_flag, sizeof(unsigned int)));
-    AT_CUDA(cudaMemset(g_err_flag, 0, sizeof(unsigned int)));
-    int dev = 0;
-    AT_CUDA(cudaGetDevice(&dev));
-    AT_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    AT_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-  }
+  const DevCtx* dc = nullptr;
+  AT_TRY(dev_ctx(&dc));
+  const int g_num_sms = dc->num_sms;
+  unsigned int* const g_err_flag = dc->err_flag;
+  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel, SMEM_LIMIT));
   AttnTcParams p;
   p.n_heads = a.n_heads; p.lq = a.lq; p.lk = a.lk;
   p.lk_pad = (a.lk + 15) & ~15;

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <math.h>
+#include <atomic>
 
 namespace artalk {
 
@@ -24,7 +25,16 @@ void set_last_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
-extern unsigned long long g_launch_count;      // kernels launched by this library (bench.py's gpu_launches)
+// Per-device state shared by the launchers: the library may drive several GPUs of one process (one engine per device), so
+// SM counts, the barrier-timeout flag the tcgen05 kernels report into, and the "dynamic shared memory opt-in done" marks are
+// kept per device ordinal (a process-wide static would hand device 1 a pointer allocated on device 0).
+struct DevCtx { int dev; int num_sms; unsigned int* err_flag; };
+int dev_ctx(const DevCtx** out);                          // context of the CURRENT device, created on first use
+int ensure_dyn_smem(const void* kernel, int bytes);       // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel)
+int& per_device_slot(int (&slots)[16]);                    // slots[current device] (ordinals >= 16 share the last slot)
+
+extern std::atomic<unsigned long long> g_launch_count;      // kernels launched by this library (bench.py's gpu_launches)
+extern std::atomic<unsigned int> g_option_epoch;            // bumped by artalk_set_option / artalk_enable_pdl: captured graphs are stale
 // optional launch trace (artalk_trace_begin/end): one CUDA event after every launch on the launching stream `st`;
 // the time between consecutive events (kernel + any idle gap before it) is attributed to the launching function.
 extern bool g_trace_on;
@@ -32,7 +42,7 @@ extern int g_trace_dims[3];              // set by launchers that want their pro
 void trace_event(const char* func, cudaStream_t st);
 #define AT_LAUNCH_CHECK()                                         \
   do {                                                            \
-    ++::artalk::g_launch_count;                                   \
+    ::artalk::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
     if (::artalk::g_trace_on) ::artalk::trace_event(__func__, st); \
     AT_CUDA(cudaGetLastError());                                  \
   } while (0)

@@ -10,6 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
+#include <mutex>
+#include <set>
 #include "engine.cuh"
 
 namespace artalk {
@@ -49,17 +52,18 @@ const Tensor* Engine::find(const std::string& name) const {
 
 int Engine::finalize() {
   const EngineConfig& c = cfg;
-  AT_REQUIRE(c.precision == 0 || c.precision == 1, "precision must be 0 (fp32) or 1 (bf16)");
+  AT_REQUIRE(c.precision >= 0 && c.precision <= 3, "precision must be 0 (fp32), 1 (bf16), 2 (bf16x3) or 3 (bf16x6)");
   AT_REQUIRE(c.embed_dim == 768 && c.embed_dim / c.ar_heads == 64, "AR width must be 768 with 64-d heads");
   AT_REQUIRE(c.vae_hidden == 512 && c.vae_hidden / c.vae_heads == 64, "VAE width must be 512 with 64-d heads");
   AT_REQUIRE(c.code_dim == 32 && c.motion_dim == 106, "code_dim 32 / motion_dim 106 expected");
   AT_REQUIRE(c.w2v_hidden == 1024 && c.w2v_conv_dim == 512 && c.w2v_hidden / c.w2v_heads == 64, "wav2vec dims");
   AT_REQUIRE(c.n_levels >= 2 && c.n_levels <= 8, "n_levels");
   AT_REQUIRE(c.style_dim == 128 && c.style_dim / c.style_heads == 32, "style encoder dims");
-  const int wt = act_dt();
-  struct Need { std::string name; int dt; int64_t numel; };
+  const int TC_W = 0x100;                  // marks the operands of tensor-core GEMMs (split into bf16 pieces in modes 2 / 3)
+  const int wt = act_dt() | TC_W;
+  struct Need { std::string name; int dt; int64_t numel; bool tc; };
   std::vector<Need> need;
-  auto req = [&](const std::string& n, int dt, int64_t numel) { need.push_back({n, dt, numel}); };
+  auto req = [&](const std::string& n, int dt, int64_t numel) { need.push_back({n, dt & 0xff, numel, (dt & TC_W) != 0}); };
   L = 0;
   for (int i = 0; i < c.n_levels; ++i) L += c.patch_nums[i];
   T = c.patch_nums[c.n_levels - 1];
@@ -148,19 +152,77 @@ int Engine::finalize() {
   for (int i = 0; i < c.n_levels; ++i) { tb.pn[i] = c.patch_nums[i]; cum += c.patch_nums[i]; tb.cum[i] = cum; }
   tb.up_i0 = get<int>("tb.up_i0"); tb.up_i1 = get<int>("tb.up_i1"); tb.up_w1 = get<float>("tb.up_w1");
   tb.pool_start = get<int>("tb.pool_start"); tb.pool_end = get<int>("tb.pool_end");
-  if (c.precision == 1 && !ar_table) {
-    std::vector<char> host(ar_layer_table_bytes(c.ar_depth));
-    for (int l = 0; l < c.ar_depth; ++l)
-      ar_layer_table_fill(host.data(), l, getw(S("ar.l%d.qkv.w", l)), getw(S("ar.l%d.proj.w", l)), getw(S("ar.l%d.ff1.w", l)),
-                          getw(S("ar.l%d.ff2.w", l)), get<float>(S("ar.l%d.qkv.b", l)), get<float>(S("ar.l%d.proj.b", l)),
-                          get<float>(S("ar.l%d.ff1.b", l)), get<float>(S("ar.l%d.ff2.b", l)), get<float>(S("ar.l%d.head_scale", l)));
-    AT_CUDA(cudaMalloc(&ar_table, host.size()));
-    AT_CUDA(cudaMemcpy(ar_table, host.data(), host.size(), cudaMemcpyHostToDevice));
-    AT_CUDA(cudaMalloc((void**)&ar_sync, 2 * sizeof(unsigned int)));
-    AT_CUDA(cudaMemset(ar_sync, 0, 2 * sizeof(unsigned int)));
+  // parity-grade mode: bf16 piece blocks of every tensor-core weight, once per weight set
+  free_split();
+  if (split_slots()) {
+    const int S = split_slots();
+    for (const Need& n : need) {
+      if (!n.tc || n.numel % 64 != 0) continue;
+      const Tensor* t = find(n.name);
+      void* d = nullptr;
+      cudaError_t e = cudaMalloc(&d, (size_t)n.numel * S * sizeof(bf16));
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_last_error("finalize: cudaMalloc of the %d piece blocks of '%s' failed: %s", S, n.name.c_str(), cudaGetErrorString(e));
+        return AT_ENOMEM;
+      }
+      wsplit[t->ptr] = d;
+      AT_TRY(launch_split_bf16((const float*)t->ptr, d, n.numel, S, 1, (cudaStream_t)0));
+    }
+    AT_CUDA(cudaDeviceSynchronize());
   }
+  drop_graphs();                            // a re-finalized engine may have new weights behind old addresses
   finalized = true;
   return AT_OK;
+}
+
+void Engine::free_split() {
+  for (auto& kv : wsplit) cudaFree(kv.second);
+  wsplit.clear();
+}
+
+// C = A W^T on the tensor cores at fp32 grade: A is split into bf16 piece blocks on the fly, W was split by finalize, and the
+// bf16 GEMM kernel runs the `slots` piece products as one GEMM with K' = slots * K (split.cu). Shapes the block layout cannot
+// express (K or a stride not a multiple of 64: the VAE decoder's 32-wide input mapping) take the fp32 CUDA-core kernel.
+int Engine::gemm_split(const GemmArgs& g, cudaStream_t st) {
+  const int S = split_slots();
+  const bool tap = g.tap_w > 0;
+  const bool shape_ok = g.K % 64 == 0 && g.ldw % 64 == 0 && g.a_map.rs % 64 == 0 && g.a_map.bs % 64 == 0 && g.w_gs % 64 == 0 &&
+                        (!tap || (g.a_gs == 64 && g.tap_w == 64)) && (tap || g.groups == 1) && !g.qkv_mode;
+  if (!shape_ok) return launch_gemm_simt(g, st);
+  auto it = wsplit.find(g.W);
+  AT_REQUIRE(it != wsplit.end(), "gemm_split: the weight operand %p is not a registered tensor-core weight", g.W);
+  int64_t extent;
+  if (g.a_map.rpb > 0) {
+    const int64_t nb = g.M / g.a_map.rpb;
+    extent = (nb - 1) * g.a_map.bs + (int64_t)(g.a_map.rpb - 1) * g.a_map.rs + (tap ? g.a_map.rs : (int64_t)g.K);
+  } else {
+    extent = (int64_t)(g.M - 1) * g.a_map.rs + g.K;
+  }
+  const size_t bytes = (size_t)extent * S * sizeof(bf16);
+  if (bytes > split_cap) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    AT_CUDA(cudaStreamIsCapturing(st, &cs));
+    AT_REQUIRE(cs == cudaStreamCaptureStatusNone, "gemm_split: operand buffer would have to grow during graph capture");
+    AT_CUDA(cudaStreamSynchronize(st));
+    if (gstream) AT_CUDA(cudaStreamSynchronize(gstream));
+    drop_graphs();                          // captured launches point into the old buffer
+    if (split_buf) { AT_CUDA(cudaFree(split_buf)); split_buf = nullptr; split_cap = 0; }
+    const size_t want = bytes + bytes / 4 + (1 << 20);
+    cudaError_t e = cudaMalloc((void**)&split_buf, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_last_error("gemm_split: cudaMalloc(%zu MiB) failed: %s", want >> 20, cudaGetErrorString(e));
+      return AT_ENOMEM;
+    }
+    split_cap = want;
+  }
+  AT_TRY(launch_split_bf16((const float*)g.A, split_buf, extent, S, 0, st));
+  GemmArgs h = g;
+  h.A = split_buf; h.a_map.rs *= S; h.a_map.bs *= S;
+  h.W = it->second; h.ldw *= S; h.w_gs *= S; h.K *= S;
+  h.tap_slots = tap ? S : 1; h.exact = 1; h.skinny = 0;
+  return launch_gemm_tc(h, st);
 }
 
 // ------------------------------------------------------------------ workspace
@@ -189,7 +251,50 @@ void* Engine::ws_alloc(size_t bytes) {
   type var = (type)ws_alloc(bytes);                       \
   if (!var) return AT_ENOMEM
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
+std::atomic<unsigned int> g_option_epoch{0};
+
+// ------------------------------------------------------------------ per-device state (common.cuh)
+namespace {
+std::mutex g_dev_mu;
+DevCtx g_dev[16];
+bool g_dev_init[16] = {};
+std::set<std::pair<int, const void*>> g_smem_done;
+int dev_slot(int dev) { return dev < 0 ? 0 : (dev > 15 ? 15 : dev); }
+}  // namespace
+
+int dev_ctx(const DevCtx** out) {
+  int dev = 0;
+  AT_CUDA(cudaGetDevice(&dev));
+  AT_REQUIRE(dev >= 0 && dev < 16, "device ordinal %d is not supported (0..15)", dev);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DevCtx& c = g_dev[dev];
+  if (!g_dev_init[dev]) {
+    c.dev = dev;
+    AT_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    AT_CUDA(cudaMalloc((void**)&c.err_flag, sizeof(unsigned int)));
+    AT_CUDA(cudaMemset(c.err_flag, 0, sizeof(unsigned int)));
+    g_dev_init[dev] = true;
+  }
+  *out = &c;
+  return AT_OK;
+}
+
+int ensure_dyn_smem(const void* kernel, int bytes) {
+  int dev = 0;
+  AT_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_smem_done.count(std::make_pair(dev, kernel))) return AT_OK;
+  AT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  g_smem_done.insert(std::make_pair(dev, kernel));
+  return AT_OK;
+}
+
+int& per_device_slot(int (&slots)[16]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return slots[dev_slot(dev)];
+}
 bool g_pdl = true;
 int g_skinny_tokens = 1;        // AR scale steps with at most this many new tokens per clip take the latency kernels (option "skinny_tokens")
 int g_pdl_mask = 3;            // measured in the chunk graph: GEMM/attention edges help (-3.4 %), elementwise edges cancel it
@@ -242,7 +347,7 @@ long trace_end(char* buf, long cap, cudaStream_t st) {
 
 int Engine::prof_begin(int enable) {
   prof = enable != 0;
-  prof_flops.clear(); prof_cls.clear();
+  prof_flops.clear(); prof_cls.clear(); prof_dims.clear();
   if (prof && prof_ev.empty()) {
     prof_ev.resize(2 * 8192);
     for (auto& e : prof_ev) AT_CUDA(cudaEventCreate(&e));
@@ -250,25 +355,30 @@ int Engine::prof_begin(int enable) {
   return AT_OK;
 }
 
-// out8 = {gemm launches, gemm ms, gemm flops, attn launches, attn ms, attn flops, dropped, 0}
+// out[16] = {gemm launches, gemm ms, gemm flops, attn launches, attn ms, attn flops, dominant GEMM shape: launches, total ms,
+//            flops per launch, M, N, K, 0...}
 int Engine::prof_read(double* out, cudaStream_t st) {
   AT_CUDA(cudaStreamSynchronize(st));
-  for (int i = 0; i < 12; ++i) out[i] = 0.0;
-  std::map<double, std::pair<double, double>> by_shape;        // GEMM flops per launch -> (launches, total ms)
+  for (int i = 0; i < 16; ++i) out[i] = 0.0;
+  std::map<std::array<int, 3>, std::pair<double, double>> by_shape;        // GEMM (M, N, K) -> (launches, total ms)
   for (size_t i = 0; i < prof_cls.size(); ++i) {
     float ms = 0.f;
     AT_CUDA(cudaEventElapsedTime(&ms, prof_ev[2 * i], prof_ev[2 * i + 1]));
     int c = prof_cls[i] * 3;
     out[c] += 1.0; out[c + 1] += ms; out[c + 2] += prof_flops[i];
-    if (prof_cls[i] == 0) { auto& e = by_shape[prof_flops[i]]; e.first += 1.0; e.second += ms; }
+    if (prof_cls[i] == 0) { auto& e = by_shape[prof_dims[i]]; e.first += 1.0; e.second += ms; }
   }
   // out[6..8]: the dominant GEMM shape (largest summed duration): launches, total ms, flops per launch
   for (auto& kv : by_shape)
-    if (kv.second.second > out[7]) { out[6] = kv.second.first; out[7] = kv.second.second; out[8] = kv.first; }
+    if (kv.second.second > out[7]) {
+      out[6] = kv.second.first; out[7] = kv.second.second;
+      out[9] = kv.first[0]; out[10] = kv.first[1]; out[11] = kv.first[2];
+      out[8] = 2.0 * out[9] * out[10] * out[11];
+    }
   return AT_OK;
 }
 
-#define PROF_WRAP(cls, flops, call)                                             \
+#define PROF_WRAP(cls, flops, d0, d1, d2, call)                                           \
   do {                                                                          \
     size_t _i = prof_cls.size();                                                \
     bool _on = prof && 2 * _i + 1 < prof_ev.size();                             \
@@ -277,6 +387,7 @@ int Engine::prof_read(double* out, cudaStream_t st) {
     if (_on) {                                                                  \
       AT_CUDA(cudaEventRecord(prof_ev[2 * _i + 1], st));                        \
       prof_cls.push_back(cls); prof_flops.push_back(flops);                     \
+      prof_dims.push_back(std::array<int, 3>{{(int)(d0), (int)(d1), (int)(d2)}}); \
     }                                                                           \
     return AT_OK;                                                               \
   } while (0)
@@ -285,12 +396,13 @@ int Engine::gemm(const GemmArgs& g0, cudaStream_t st) {
   GemmArgs g = g0;
   // latency mode: few rows and a small output (the hoisted AdaLN / previous-chunk K/V GEMMs stay on the tensor-core kernel)
   if (latency_rows > 0 && g.M <= latency_rows && (int64_t)g.M * g.N <= ((int64_t)1 << 21)) g.skinny = 1;
-  PROF_WRAP(0, 2.0 * g.M * g.N * g.K * g.groups, cfg.precision == 0 ? launch_gemm_simt(g, st) : launch_gemm_tc(g, st));
+  PROF_WRAP(0, 2.0 * g.M * g.N * g.K * g.groups, g.M, g.N * g.groups, g.K,
+            cfg.precision == 0 ? launch_gemm_simt(g, st) : (cfg.precision == 1 ? launch_gemm_tc(g, st) : gemm_split(g, st)));
 }
 
 int Engine::attention(const AttnArgs& a, cudaStream_t st) {
   double keys = (a.split > 0) ? 0.5 * (a.split + a.lk) : a.lk;     // rows < split see `split` keys, the rest see lk
-  PROF_WRAP(1, 4.0 * a.n_seq * a.n_heads * a.head_dim * a.lq * keys, launch_attention(a, st));
+  PROF_WRAP(1, 4.0 * a.n_seq * a.n_heads * a.head_dim * a.lq * keys, a.n_seq * a.n_heads, a.lq, a.lk, launch_attention(a, st));
 }
 
 // ------------------------------------------------------------------ wav2vec2
@@ -616,13 +728,14 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
   bool launched = false;
   if (can_graph) {
     auto it = graphs.find(key);
-    if (it != graphs.end() && it->second.ws_base != ws) {          // workspace was re-allocated: addresses are stale
+    // stale: the workspace was re-allocated (addresses), or a process-wide option changed which kernels a launch selects
+    if (it != graphs.end() && (it->second.ws_base != ws || it->second.epoch != g_option_epoch.load())) {
       if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
       graphs.erase(it);
       it = graphs.end();
     }
     if (it == graphs.end()) {
-      GraphEntry ge; ge.exec = nullptr; ge.ws_base = ws; ge.warm = 0; ge.n_launches = 0;
+      GraphEntry ge; ge.exec = nullptr; ge.ws_base = ws; ge.warm = 0; ge.n_launches = 0; ge.epoch = g_option_epoch.load();
       it = graphs.insert(std::make_pair(key, ge)).first;
     }
     GraphEntry& ge = it->second;
@@ -642,9 +755,12 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
       cudaError_t ce = cudaStreamEndCapture(gstream, &graph);
       ws_off = body_mark;
       if (rc != AT_OK || ce != cudaSuccess || !graph) {
-        cudaGetLastError();
+        const cudaError_t sticky = cudaGetLastError();
         if (graph) cudaGraphDestroy(graph);
-        use_graphs = false;                                          // fall back to eager launches for good
+        use_graphs = false;                                          // eager launches from here on, and say so
+        graph_failure = S("capture of the chunk graph failed (body status %d, cudaStreamEndCapture: %s / %s)", rc,
+                          cudaGetErrorString(ce), cudaGetErrorString(sticky));
+        fprintf(stderr, "[artalk_b200] WARNING: %s; this engine now launches the chunk body eagerly (slower)\n", graph_failure.c_str());
         if (rc != AT_OK) return rc;
       } else {
         if (getenv("ARTALK_DEBUG")) {
@@ -661,21 +777,27 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
         }
         cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
         cudaGraphDestroy(graph);
-        if (ie != cudaSuccess) { cudaGetLastError(); ge.exec = nullptr; use_graphs = false; }
+        if (ie != cudaSuccess) {
+          cudaGetLastError();
+          ge.exec = nullptr; use_graphs = false;
+          graph_failure = S("cudaGraphInstantiate of the chunk graph failed: %s", cudaGetErrorString(ie));
+          fprintf(stderr, "[artalk_b200] WARNING: %s; this engine now launches the chunk body eagerly (slower)\n", graph_failure.c_str());
+        }
       }
     }
     if (ge.exec) {
       AT_CUDA(cudaEventRecord(gev_in, st));
       AT_CUDA(cudaStreamWaitEvent(gstream, gev_in, 0));
       AT_CUDA(cudaGraphLaunch(ge.exec, gstream));
+      ++graph_replays;
       AT_CUDA(cudaEventRecord(gev_out, gstream));
       AT_CUDA(cudaStreamWaitEvent(st, gev_out, 0));
-      g_launch_count += ge.n_launches;
+      g_launch_count.fetch_add(ge.n_launches, std::memory_order_relaxed);
       launched = true;
     } else if (use_graphs) {
-      unsigned long long l0 = g_launch_count;
+      unsigned long long l0 = g_launch_count.load();
       AT_TRY(ar_chunk_body(B, scond, style_ws, prev_ws, motion_ws, words_ws, logits_ws, forced_words ? forced_ws : nullptr, enc_ws, st));
-      ge.n_launches = g_launch_count - l0;
+      ge.n_launches = g_launch_count.load() - l0;
       ge.warm++;
       launched = true;
     }
@@ -746,21 +868,6 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
     const uint32_t* src_words = forced_words ? forced_words : words;
     AT_TRY(launch_bits_tokens(tb, src_words, L, style, get<float>("ar.embed.w"), get<float>("ar.embed.b"), get<float>("ar.lvl_pos"), x,
                               DT_F32, B, p, p, C, st));
-    if (defer && ar_table && ar_small_supported(B, n_new, C, P + off + n_new, 2 * c.code_dim)) {
-      // few new tokens per clip: every block + the head in one launch (skinny.cu)
-      ArSmallArgs sa;
-      sa.B = B; sa.n_new = n_new; sa.C = C; sa.NL = NL; sa.lk = P + off + n_new; sa.n_logits = 2 * c.code_dim;
-      sa.x = x; sa.y = ybuf; sa.u = u; sa.qbuf = qbuf; sa.o = o; sa.f = f;
-      sa.ada = ada_p; sa.ada_map = ada_map;
-      sa.kcache = kcache; sa.vcache = vcache; sa.kv_layer_stride = (int64_t)B * KV * C; sa.kv_seq_stride = (int64_t)KV * C;
-      sa.kv_new_off = (int64_t)(P + off) * C; sa.kv_new_map = batched_rows(n_new, (int64_t)KV * C, C);
-      sa.layer_table = ar_table; sa.whead = getw("ar.head.w"); sa.bhead = get<float>("ar.head.b");
-      sa.logits = logits + (size_t)off * 2 * c.code_dim; sa.logits_map = batched_rows(n_new, (int64_t)L * 2 * c.code_dim, 2 * c.code_dim);
-      sa.sync = ar_sync; sa.eps = 1e-6f;
-      AT_TRY(launch_ar_small(sa, st));
-      AT_TRY(launch_argmax_bits(logits + (size_t)off * 2 * c.code_dim, sa.logits_map, words + off, batched_rows(n_new, L, 1), M, st));
-      continue;
-    }
     bool pending = false;                                    // ybuf holds the previous layer's FFN2 output, gate gamma2 of that layer
     for (int l = 0; l < NL; ++l) {
       const char* ada_l = ada_p + (size_t)l * 6 * C * s;     // chunk order: g1, g2, s1, s2, b1, b2 (quirk 9)

@@ -2,6 +2,7 @@
 // forward passes of the path. One Engine per (device, weight set); not thread-safe; all work is enqueued on the
 // caller's stream.
 #pragma once
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -10,7 +11,9 @@
 namespace artalk {
 
 struct EngineConfig {        // mirrors artalk_config_t in include/artalk_b200.h
-  int precision;             // 0 = fp32 (CUDA-core GEMM), 1 = bf16 (tcgen05 GEMM, fp32 accumulate)
+  int precision;             // 0 = fp32 (CUDA-core GEMM), 1 = bf16 (tcgen05 GEMM, fp32 accumulate),
+                             // 2 / 3 = parity-grade tensor-core mode: fp32 data flow, tcgen05 GEMMs on 2 / 3 bf16 pieces per
+                             // operand (3 / 6 MMA passes, split.cu)
   int ar_depth, ar_heads, embed_dim, cond_dim;
   int vae_depth, vae_heads, vae_hidden, code_dim, motion_dim;
   int n_levels; int patch_nums[8];
@@ -34,7 +37,14 @@ struct Engine {
   BitsTables tb;
   // derived
   int L = 0, T = 0, n_audio_frames = 0; int conv_len[8];
-  int act_dt() const { return cfg.precision == 0 ? DT_F32 : DT_BF16; }
+  int act_dt() const { return cfg.precision == 1 ? DT_BF16 : DT_F32; }
+  int split_slots() const { return cfg.precision == 2 ? 3 : (cfg.precision == 3 ? 6 : 0); }
+  // parity-grade mode: bf16 piece blocks of every tensor-core weight (owned, built by finalize) keyed by the fp32 tensor's
+  // device pointer, and a grow-on-demand buffer for the piece blocks of the current GEMM's A operand
+  std::map<const void*, void*> wsplit;
+  char* split_buf = nullptr; size_t split_cap = 0;
+  int gemm_split(const GemmArgs& g, cudaStream_t st);
+  void free_split();
 
   int set_tensor(const char* name, void* ptr, int dt, int64_t numel);
   int finalize();
@@ -50,7 +60,7 @@ struct Engine {
   int attention(const AttnArgs& a, cudaStream_t st);
   // optional CUDA-event instrumentation of the GEMM / attention launches (bench.py roofline pass)
   bool prof = false;
-  std::vector<cudaEvent_t> prof_ev; std::vector<double> prof_flops; std::vector<int> prof_cls;
+  std::vector<cudaEvent_t> prof_ev; std::vector<double> prof_flops; std::vector<int> prof_cls; std::vector<std::array<int, 3>> prof_dims;
   int prof_begin(int enable);
   int prof_read(double* out8, cudaStream_t st);
 
@@ -67,12 +77,14 @@ struct Engine {
   int ar_chunk_body(int n_clips, const char* scond, const float* style, uint32_t* prev_words, float* motion_out,
                     uint32_t* words, float* logits, const uint32_t* forced_words, float* enc_out, cudaStream_t st);
   // CUDA graphs of the chunk body, keyed by (clips, teacher forcing); valid while the workspace base is unchanged
-  struct GraphEntry { cudaGraphExec_t exec; char* ws_base; int warm; unsigned long long n_launches; };
+  struct GraphEntry { cudaGraphExec_t exec; char* ws_base; int warm; unsigned long long n_launches; unsigned int epoch; };
+  // set when a capture / instantiation failed: the engine then launches eagerly (correct, ~10-15 % slower at batch 64, several
+  // times slower at batch 1) and says so: once on stderr, and to the host through artalk_graph_status
+  std::string graph_failure;
+  int graph_replays = 0;
   std::map<int, GraphEntry> graphs;
   bool use_graphs = true;
   cudaStream_t gstream = nullptr; cudaEvent_t gev_in = nullptr, gev_out = nullptr;
-  // whole-stack kernel of the few-token scale steps (skinny.cu): per-block weight pointer table + barrier words (device)
-  void* ar_table = nullptr; unsigned int* ar_sync = nullptr;
   int latency_rows = 0;      // artalk_set_latency_mode: GEMMs with at most this many rows take the latency kernel (0 = off)
   void drop_graphs() {
     for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);

@@ -281,8 +281,6 @@ __global__ void __launch_bounds__(256) flame_pack_kernel(const float* __restrict
   }
 }
 
-unsigned int* g_err_flag = nullptr;
-int g_num_sms = 0;
 int g_flame_v2 = 0;       // option "flame_v2": packed-pair skinning epilogue with pipelined accumulator reads (opt-in until measured)
 }  // namespace
 
@@ -293,15 +291,12 @@ int launch_flame_tc(const FlameModel& m, const float* base, const float* coef, i
                     const void* b_split, int KS, void* a_split_ws, float* verts, int n_frames, cudaStream_t st) {
   if (n_frames <= 0) return AT_OK;
   AT_REQUIRE(KS % 64 == 0 && KS >= n_l && b_split && a_split_ws, "flame_tc: bad split operands");
-  if (!g_err_flag) {
-    AT_CUDA(cudaMalloc((void**)&g_err_flag, sizeof(unsigned int)));
-    AT_CUDA(cudaMemset(g_err_flag, 0, sizeof(unsigned int)));
-    int dev = 0;
-    AT_CUDA(cudaGetDevice(&dev));
-    AT_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    AT_CUDA(cudaFuncSetAttribute(flame_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    AT_CUDA(cudaFuncSetAttribute(flame_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  }
+  const DevCtx* dc = nullptr;
+  AT_TRY(dev_ctx(&dc));
+  const int g_num_sms = dc->num_sms;
+  unsigned int* const g_err_flag = dc->err_flag;
+  AT_TRY(ensure_dyn_smem((const void*)flame_tc_kernel<false>, SMEM_BYTES));
+  AT_TRY(ensure_dyn_smem((const void*)flame_tc_kernel<true>, SMEM_BYTES));
   const int64_t total = (int64_t)n_frames * KS;
   int pgrid = (int)((total + 255) / 256);
   if (pgrid > 148 * 16) pgrid = 148 * 16;

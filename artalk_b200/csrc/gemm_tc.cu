@@ -36,7 +36,9 @@ struct TcParams {
   int tma_out;             // pair kernel: fp32 output chunks leave by TMA store from the warp's scratch (plain [M, N] out32 only)
   int tma_resid;           // pair kernel, EPI 1: the fp32 residual tile arrives by TMA (plain [M, N] residual, N % 32 == 0)
   int num_kb;              // K blocks of 64
-  int tap_mode, tap_pad;   // tap mode: k-block j reads rows shifted by (j - tap_pad), columns of group g
+  int tap_mode, tap_pad;   // tap mode: k-block j reads rows shifted by (j / tap_slots - tap_pad), columns of group g (piece slot j % tap_slots)
+  int tap_slots;
+  int exact;               // libm-accurate activations (parity-grade mode)
   int a_group_cols;        // column offset per group in the A view (tap mode)
   int64_t c_gs; int bias_gs;
   const float* bias; int act;
@@ -231,6 +233,12 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
       }
     }
     // ---- activation (switch hoisted out of the element loop; fast-math variants: outputs are rounded to bf16)
+    if (p.exact) {
+      if (p.act != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+      }
+    } else
     switch (p.act) {
       case ACT_GELU_ERF:
 #pragma unroll
@@ -447,7 +455,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
             mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(A_STAGE_BYTES + bn * BK * 2));
           }
-          if (p.tap_mode) tma_load_3d(sa, &tmA, full_bar(stage), g * p.a_group_cols, mt * BM + kb - p.tap_pad, b);
+          if (p.tap_mode) {
+            const int tap = kb / p.tap_slots, slot = kb - tap * p.tap_slots;
+            tma_load_3d(sa, &tmA, full_bar(stage), (g * p.a_group_cols) * p.tap_slots + slot * BK, mt * BM + tap - p.tap_pad, b);
+          }
           else tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, mt * BM, b);
           if (!w_done) tma_load_3d(sb, bn == BN ? &tmW : &tmWt, full_bar(stage), kb * BK, col_base, g);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -893,8 +904,7 @@ int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint
   return AT_OK;
 }
 
-unsigned int* g_err_flag = nullptr;
-int g_num_sms = 0;
+thread_local int g_num_sms = 0;          // SM count of the current device, refreshed from dev_ctx() at every launch
 extern int g_tma_out;
 
 // Output tensor map for the TMA-store epilogue: (cols, rows per batch, batches), 32 x 32 boxes, so rows a tile computes past
@@ -919,11 +929,7 @@ template <int BN, int EPI>
 int launch_bn_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmO, const TcParams& p,
                   cudaStream_t st) {
   using Cfg = TileCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  AT_TRY(ensure_dyn_smem((const void*)gemm_tc_kernel<BN, EPI>, Cfg::SMEM_BYTES));
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   g_trace_dims[0] = p.rpb * p.n_batches; g_trace_dims[1] = p.N; g_trace_dims[2] = p.num_kb * BK * p.groups;
   AT_CUDA(launch_k(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, tmA, tmW, tmWt, tmO, p));
@@ -944,9 +950,10 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
 template <int EPI, int RB = 1>
 int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmR,
                     const CUtensorMap& tmO, const TcParams& p, cudaStream_t st) {
-  static int max_clusters = -1;
+  static int max_clusters_dev[16] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  int& max_clusters = per_device_slot(max_clusters_dev);
   if (max_clusters < 0) {
-    AT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    AT_TRY(ensure_dyn_smem((const void*)gemm_tc2_kernel<EPI, RB>, SMEM2_BYTES));
     cudaLaunchConfig_t qc = {};
     qc.gridDim = dim3(g_num_sms & ~1); qc.blockDim = dim3(384); qc.dynamicSmemBytes = SMEM2_BYTES;
     cudaLaunchAttribute qa[1];
@@ -986,8 +993,11 @@ void set_gemm_band_mb(int mb) { g_band_mb = mb; }
 void set_gemm_tma_out(int on) { g_tma_out = on; }
 void set_gemm_resid_deep(int on) { g_resid_deep = on; }
 
-int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
+  GemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0) return AT_OK;
+  // an fp32 "activation" output alone is just the fp32 output (parity-grade mode keeps activations in fp32): TMA-store epilogue
+  if (!g.out32 && g.out_act && g.out_act_dt == DT_F32) { g.out32 = (float*)g.out_act; g.out_act = nullptr; }
   AT_REQUIRE(g.A && g.W && (g.out32 || g.out_act || g.qkv_mode), "gemm_tc: null operand");
   AT_REQUIRE(g.K > 0 && g.K % 16 == 0, "gemm_tc: K=%d must be a positive multiple of 16", g.K);
   AT_REQUIRE(g.ldw % 8 == 0 && g.a_map.rs % 8 == 0 && g.a_map.bs % 8 == 0 && g.a_gs % 8 == 0 && g.w_gs % 8 == 0,
@@ -996,13 +1006,10 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
   AT_REQUIRE(g.tap_w == 0 || (g.tap_w == BK && g.a_map.rpb > 0 && g.K % BK == 0), "gemm_tc: tap mode needs tap_w == 64");
   AT_REQUIRE(g.groups == 1 || g.tap_w > 0, "gemm_tc: groups are only supported in tap mode");
   if (g.skinny && gemm_skinny_supported(g)) return launch_gemm_skinny(g, st);      // latency-bound shapes (few rows): skinny.cu
-  if (!g_err_flag) {
-    AT_CUDA(cudaMalloc((void**)&g_err_flag, sizeof(unsigned int)));
-    AT_CUDA(cudaMemset(g_err_flag, 0, sizeof(unsigned int)));
-    int dev = 0;
-    AT_CUDA(cudaGetDevice(&dev));
-    AT_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const DevCtx* dc = nullptr;
+  AT_TRY(dev_ctx(&dc));
+  g_num_sms = dc->num_sms;
+  unsigned int* const g_err_flag = dc->err_flag;
   TcParams p;
   p.tma_resid = 0; p.band_n = 0; p.tma_out = 0;
   p.N = g.N;
@@ -1030,7 +1037,7 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
       p.main_tiles = (int)tiles2 - (split2 > 1 ? rem2 : 0); p.tail_split = split2; p.tail_bn = 256 / split2;
       p.total_tiles = p.main_tiles + (split2 > 1 ? rem2 * split2 : 0);
       p.num_kb = ceil_div(g.K, BK);
-      p.tap_mode = 0; p.tap_pad = 0; p.a_group_cols = 0;
+      p.tap_mode = 0; p.tap_pad = 0; p.a_group_cols = 0; p.tap_slots = 1; p.exact = g.exact;
       p.c_gs = 0; p.bias_gs = 0; p.bias = g.bias; p.act = g.act;
       p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
       p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;
@@ -1110,7 +1117,8 @@ int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     p.total_tiles = p.main_tiles + rem * tail_split;
   }
   p.num_kb = ceil_div(g.K, BK);
-  p.tap_mode = g.tap_w > 0 ? 1 : 0; p.tap_pad = g.tap_pad; p.a_group_cols = (int)g.a_gs;
+  p.tap_mode = g.tap_w > 0 ? 1 : 0; p.tap_pad = g.tap_pad; p.a_group_cols = (int)g.a_gs; p.tap_slots = g.tap_slots > 0 ? g.tap_slots : 1;
+  p.exact = g.exact;
   p.c_gs = g.c_gs; p.bias_gs = g.bias_gs; p.bias = g.bias; p.act = g.act;
   p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
   p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;

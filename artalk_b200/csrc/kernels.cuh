@@ -55,6 +55,10 @@ struct GemmArgs {
   // shapes (tokens per clip of the scale step), never by the batch, so that a clip's arithmetic does not depend on how
   // many clips run with it (batched == per-clip loop stays bit-exact in bf16 mode)
   int skinny;
+  // parity-grade mode (split.cu): operands are bf16 piece blocks, K = slots * K_fp32. tap_slots: in tap mode every 64-column
+  // block of an A row holds `tap_slots` consecutive piece blocks and k-block kb reads slot kb % tap_slots of tap kb / tap_slots.
+  // exact: activations use the libm-accurate functions (erff / tanhf / expf) instead of the bf16-grade fast forms
+  int tap_slots; int exact;
 };
 static inline GemmArgs gemm_args() {
   GemmArgs g;
@@ -64,7 +68,7 @@ static inline GemmArgs gemm_args() {
   g.resid = nullptr; g.resid_map = plain_rows(0); g.out32 = nullptr; g.out_act = nullptr; g.out_act_dt = DT_F32;
   g.c_map = plain_rows(0);
   g.qkv_mode = 0; g.qkv_C = 0; g.head_scale = nullptr; g.qbuf = nullptr; g.kcache = nullptr; g.vcache = nullptr;
-  g.kv_map = plain_rows(0); g.kv_layer_stride = 0; g.skinny = 0;
+  g.kv_map = plain_rows(0); g.kv_layer_stride = 0; g.skinny = 0; g.tap_slots = 1; g.exact = 0;
   return g;
 }
 // fp32 CUDA-core GEMM (A and W fp32). gemm_simt.cu
@@ -83,6 +87,11 @@ bool gemm_skinny_supported(const GemmArgs& g);
 int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st);
 void set_skinny_max_m(int v);
 
+// ---------------- split.cu ----------------
+// fp32 [n_elems] -> bf16 piece blocks [n_elems / 64][slots][64] (slots 3: 2 pieces / 3 MMA passes, 6: 3 pieces / 6 passes);
+// is_w selects the weight-side slot order so that slot s of A times slot s of W enumerates the kept piece products
+int launch_split_bf16(const float* x, void* out, int64_t n_elems, int slots, int is_w, cudaStream_t st);
+
 // ---------------- attention.cu ----------------
 struct AttnArgs {
   const void* q; const void* k; const void* v; void* out;   // dtype dt
@@ -100,33 +109,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t st);
 bool attention_tc_supported(const AttnArgs& a);
 void set_attn_simt_max_lq(int v);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
-// bf16, head_dim 64, <= 8 query rows, <= 256 keys, no split mask: one CTA per (sequence, head). skinny.cu
-bool attention_few_supported(const AttnArgs& a);
-int launch_attention_few(const AttnArgs& a, cudaStream_t st);
-void set_attn_few_max_lq(int v);
 // AR q/k/v post-processing (app/transformer.py:71-74): per-head L2 normalise q (x exp(min(scale_mul, ln100))) and k,
 // q -> qbuf [M, C]; k,v -> cache rows given by kv_map. qkv: [M, 3C] (q | k | v), or [M, 2C] (k | v) when has_q = 0.
 int launch_qkv_norm_scatter(const void* qkv, int dt, int64_t qkv_rs, int has_q, const float* head_scale, void* qbuf,
                             void* kcache, void* vcache, RowMap kv_map, int rows, int n_heads, cudaStream_t st);
-
-// whole-stack kernel for AR scale steps with <= 8 new tokens per clip (skinny.cu): every block + the head in one launch
-struct ArSmallArgs {
-  int B, n_new, C, NL, lk, n_logits;           // lk = resident keys (previous chunk + every current token of scale <= this)
-  float* x; float* y; void* u; void* qbuf; void* o; void* f;       // [B*n_new, C] (f: 4C) workspace; x holds the input tokens
-  const void* ada; RowMap ada_map;              // bf16 AdaLN table rows of this scale, block 0
-  void* kcache; void* vcache; int64_t kv_layer_stride, kv_seq_stride;   // caches of block 0, key row 0
-  int64_t kv_new_off; RowMap kv_new_map;        // new token row r lives at kv_new_off + kv_new_map.off(r)
-  const void* layer_table;                      // device array built with ar_layer_table_fill
-  const void* whead; const float* bhead; float* logits; RowMap logits_map;
-  unsigned int* sync;                           // 2 zero-initialised device words
-  float eps;
-};
-bool ar_small_supported(int B, int n_new, int C, int lk, int n_logits);
-int launch_ar_small(const ArSmallArgs& a, cudaStream_t st);
-size_t ar_layer_table_bytes(int n_layers);
-void ar_layer_table_fill(void* host_dst, int l, const void* wqkv, const void* wproj, const void* wff1, const void* wff2, const float* bqkv,
-                         const float* bproj, const float* bff1, const float* bff2, const float* head_scale);
-void set_ar_small(int on);
 
 // ---------------- bits.cu ----------------
 struct ScaleOps;   // device tables of the up/down-sampling operators, built by bits_build_tables

@@ -2,18 +2,21 @@
 // window 5 / poly 2 on every dim, window 9 / poly 3 on dims 100:103, scipy mode 'interp' (edge samples come from
 // the polynomial fitted to the first / last window). The hat matrices H5, H9 (row i = weights giving the fitted
 // value at window position i) are built on the host in fp64 and passed by value.
+#include <mutex>
 #include "kernels.cuh"
 
 namespace artalk {
 
 struct SavgolTables { float h5[5][5]; float h9[9][9]; };
 static SavgolTables g_tables;
-static bool g_tables_set = false;
+static std::atomic<bool> g_tables_set{false};
+static std::mutex g_tables_mu;      // the tables are constants of the filter; concurrent engines may race to set them
 
 void set_savgol_tables(const float* h5, const float* h9) {
+  std::lock_guard<std::mutex> lk(g_tables_mu);
   for (int i = 0; i < 25; ++i) (&g_tables.h5[0][0])[i] = h5[i];
   for (int i = 0; i < 81; ++i) (&g_tables.h9[0][0])[i] = h9[i];
-  g_tables_set = true;
+  g_tables_set.store(true, std::memory_order_release);
 }
 
 template <int W>
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(256) savgol_post_kernel(const float* __restric
 int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int T_out, int dim, int fix_pose,
                        int zero_tail, cudaStream_t st) {
   if (n_clips <= 0 || T_out <= 0) return AT_OK;
-  AT_REQUIRE(g_tables_set, "savgol: tables not set");
+  AT_REQUIRE(g_tables_set.load(std::memory_order_acquire), "savgol: tables not set");
   AT_REQUIRE(T >= 9, "savgol: window_length 9 must be <= number of frames (%d)", T);
   AT_REQUIRE(T_out <= T && dim == 106, "savgol: bad shape");
   int64_t total = (int64_t)n_clips * T_out * dim;

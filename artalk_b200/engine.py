@@ -45,15 +45,14 @@ def smooth_motion(motion: torch.Tensor, clip_length: Optional[int] = None, fix_p
         raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
     T_out = T if clip_length is None else max(0, min(T, int(clip_length)))
     out = torch.empty(B, T_out, D, device=m.device)
-    _lib.check(_lib.lib().artalk_smooth_motion(m.data_ptr(), out.data_ptr(), B, T, T_out, int(bool(fix_pose)),
-                                               int(bool(zero_tail)), _lib.stream_ptr(m.device)))
+    _lib.call(m.device, _lib.lib().artalk_smooth_motion, m.data_ptr(), out.data_ptr(), B, T, T_out, int(bool(fix_pose)),
+              int(bool(zero_tail)), _lib.stream_ptr(m.device))
     return out[0] if squeeze else out
 
 
 class ARTAvatarInferEngine:
     def __init__(self, load_gaga=False, fix_pose=False, clip_length=750, device="cuda", *, precision="bf16",
-                 state_dict=None, config=None, flame_asset=None, wav2vec=None, make_output_dir=True, lanes=1,
-                 latency_mode=False):
+                 state_dict=None, config=None, flame_asset=None, wav2vec=None, make_output_dir=True, latency_mode=False):
         if load_gaga:
             raise NotImplementedError("GAGAvatar rendering is outside the audio->motion path (use load_gaga=False)")
         self.device = device
@@ -65,7 +64,7 @@ class ARTAvatarInferEngine:
         configs = config if config is not None else json.load(open("./assets/config.json"))
         configs = json.loads(json.dumps(configs))
         configs["AR_CONFIG"]["AUDIO_ENCODER"] = audio_encoder
-        self.ARTalk = BitwiseARModel(configs, device=device, precision=precision, wav2vec=wav2vec, lanes=lanes).eval().to(device)
+        self.ARTalk = BitwiseARModel(configs, device=device, precision=precision, wav2vec=wav2vec).eval().to(device)
         self.ARTalk.load_state_dict(ckpt, strict=True)
         if latency_mode:                               # batch-1 / few-clip streaming: see BitwiseARModel.set_latency_mode
             self.ARTalk.set_latency_mode(True)
@@ -122,14 +121,18 @@ class ARTAvatarInferEngine:
         decoded immediately with the AR state carried across chunks; see ``StreamingSession``."""
         return StreamingSession(self, batch)
 
-    def mesh_vertices(self, pred_motions, shape_code=None):
-        """The vertices the mesh branch of ``rendering`` computes (inference.py:62-69): (N,106) -> (N,5023,3)."""
+    def mesh_vertices(self, pred_motions, shape_code=None, out=None):
+        """The vertices the mesh branch of ``rendering`` computes (inference.py:62-69): (N,106) -> (N,5023,3). ``out``: optional
+        preallocated (N,5023,3) fp32 device tensor (batch jobs decode 10^5 frames per call: 60 KB per frame)."""
         if shape_code is None:
             shape_code = pred_motions.new_zeros(1, 300).to(self.device).expand(pred_motions.shape[0], -1)
         else:
             assert shape_code.dim() == 2, f"Invalid shape_code dim: {shape_code.dim()}."
             assert shape_code.shape[0] == 1, f"Invalid shape_code shape: {shape_code.shape}."
             shape_code = shape_code.to(self.device).expand(pred_motions.shape[0], -1)
+        if out is not None:                     # get_flame_verts(with_global=True) for a 2-D shape code, writing in place
+            return self.flame_model(shape_params=shape_code, expression_params=pred_motions[..., :100],
+                                    pose_params=pred_motions[..., 100:], out=out)
         return self.ARTalk.basic_vae.get_flame_verts(self.flame_model, shape_code, pred_motions, with_global=True)
 
     def rendering(self, audio, pred_motions, shape_id="mesh", shape_code=None, save_name="ARTAvatar.mp4"):

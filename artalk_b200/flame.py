@@ -14,6 +14,7 @@ from . import _lib
 
 class FLAMEModel:
     N_JOINTS = 5
+    MAX_FRAMES = 65536
 
     def __init__(self, n_shape, n_exp, scale=1.0, no_lmks=False, lmks_type="lmks70", *, asset=None, asset_path=None,
                  device="cuda", precision="tc"):
@@ -95,7 +96,7 @@ class FLAMEModel:
     def __call__(self, *a, **k):
         return self.forward(*a, **k)
 
-    def forward(self, shape_params=None, expression_params=None, pose_params=None, eye_pose_params=None, verts_sclae=None):
+    def forward(self, shape_params=None, expression_params=None, pose_params=None, eye_pose_params=None, verts_sclae=None, out=None):
         """shape (N,n_shape), expression (N,n_exp), pose (N,6) [global rot, jaw] or (N,3) [jaw] -> (N,V,3)*scale."""
         lib = _lib.lib()
         N = shape_params.shape[0]
@@ -119,12 +120,19 @@ class FLAMEModel:
         if shape_params.shape[1] != self._c.n_shape or expr.shape[1] != self._c.n_exp or pose.shape[1] != 6:
             raise ValueError("bad FLAME parameter widths: shape %s expr %s pose %s" %
                              (tuple(shape_params.shape), tuple(expr.shape), tuple(pose.shape)))
-        need = lib.artalk_flame_workspace_floats(C.byref(self._c), N)
+        verts = torch.empty(N, self.n_verts, 3, dtype=torch.float32, device=dev) if out is None else out
+        if tuple(verts.shape) != (N, self.n_verts, 3) or verts.dtype != torch.float32 or not verts.is_contiguous():
+            raise ValueError("out must be a contiguous (N, %d, 3) fp32 tensor" % self.n_verts)
+        # long clips / big batches go through in launches of at most MAX_FRAMES frames (bounded workspace: 1.7 KB per frame)
+        step = self.MAX_FRAMES
+        need = lib.artalk_flame_workspace_floats(C.byref(self._c), min(N, step))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.float32, device=dev)
-        verts = torch.empty(N, self.n_verts, 3, dtype=torch.float32, device=dev)
-        _lib.check(lib.artalk_flame_vertices(
-            C.byref(self._c), shape_params.data_ptr(), 0 if shared_shape else shape_params.stride(0),
-            expr.data_ptr(), expr.stride(0), pose.data_ptr(), pose.stride(0), 0, self._ws.data_ptr(), verts.data_ptr(), N,
-            _lib.stream_ptr(dev)))
+        for i0 in range(0, N, step):
+            n = min(step, N - i0)
+            sp = shape_params if shared_shape else shape_params[i0:i0 + n]
+            _lib.call(dev, lib.artalk_flame_vertices,
+                      C.byref(self._c), sp.data_ptr(), 0 if shared_shape else shape_params.stride(0),
+                      expr[i0:i0 + n].data_ptr(), expr.stride(0), pose[i0:i0 + n].data_ptr(), pose.stride(0), 0, self._ws.data_ptr(),
+                      verts[i0:i0 + n].data_ptr(), n, _lib.stream_ptr(dev))
         return verts

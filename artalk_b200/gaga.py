@@ -46,7 +46,7 @@ class GagaPointBuilder:
         pts = self.flame(shape_params=self.shapecode.expand(N, -1), pose_params=pose_code, expression_params=exp_code,
                          eye_pose_params=m.new_zeros(N, 6)).float()
         if self.idx.numel():
-            _lib.check(_lib.lib().artalk_ema_scan(pts.data_ptr(), pts.stride(0), self.idx.data_ptr(), self.idx.numel(), N,
-                                                  self.state.data_ptr(), int(self.has_state), self.keep, _lib.stream_ptr(self.device)))
+            _lib.call(self.device, _lib.lib().artalk_ema_scan, pts.data_ptr(), pts.stride(0), self.idx.data_ptr(), self.idx.numel(), N,
+                                                  self.state.data_ptr(), int(self.has_state), self.keep, _lib.stream_ptr(self.device))
         self.has_state = True
         return pts

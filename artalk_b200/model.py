@@ -5,10 +5,11 @@ arithmetic runs in libartalk_b200.so. Differences from the reference that are pa
 * batches of clips are accepted (the reference asserts batch 1, app/models.py:65); batched == per-clip loop;
 * wav2vec2 runs for every chunk of every clip up front; the scale loop uses a KV cache, hoisted AdaLN and
   once-per-chunk previous-chunk K/V (SURVEY F2) — outputs equal the un-cached reference schedule;
-* clips are independent, so a batch can be split over ``lanes`` engine handles (shared weights, private workspace /
-  CUDA graphs) running on their own streams. Measured on B200 (64 clips x 10 s): 1 lane 185.9k, 2 lanes 179.6k frames/s —
-  the persistent 148-CTA GEMMs of one lane hold every SM for their whole duration, so the other lane's small kernels
-  queue behind them; the default is therefore one lane.
+* ``precision``: "bf16" (tcgen05, default), "fp32" (CUDA cores), "bf16x3" / "bf16x6" (tcgen05 at fp32 grade: every GEMM
+  operand split into 2 / 3 bf16 pieces, fp32 data flow; the tensor-core mode that meets the reference's bit-exact contract).
+
+Every C-ABI call is made with the model's device current (``torch.cuda.device``), so an engine on ``cuda:1`` works while the
+process's current device is 0.
 """
 from __future__ import annotations
 
@@ -72,37 +73,35 @@ class BitwiseVAE:
 
 class BitwiseARModel:
     def __init__(self, model_cfg=None, *, device="cuda", precision="bf16", wav2vec: Optional[Wav2VecConfig] = None,
-                 max_clips: int = 256, lanes: int = 1, min_lane_clips: int = 8, **kwargs):
+                 max_clips: int = 256, **kwargs):
         if isinstance(model_cfg, ModelConfig):
             self.cfg = model_cfg
         else:
             self.cfg = ModelConfig.from_reference_json(model_cfg, wav2vec=wav2vec)
         self.cfg.validate()
         if precision not in _lib.PRECISION:
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISION))
         self.precision = precision
         self._device = torch.device(device)
         self.max_clips = int(max_clips)
-        self.lanes = max(1, int(lanes))
-        self.min_lane_clips = int(min_lane_clips)
         self.patch_nums = list(self.cfg.patch_nums)
         self.attn_depth = self.cfg.ar_depth
         self.prev_ratio = self.cfg.prev_ratio
         self.audio_feature_dim = self.cfg.cond_dim
         self.basic_vae = BitwiseVAE(self)
-        self._hs: List[C.c_void_p] = []
-        self._streams: List[torch.cuda.Stream] = []
+        self._h: Optional[C.c_void_p] = None
         self._tensors: Dict[str, torch.Tensor] = {}
         self._init_words = None
         self.latency_rows = 0
         self._copy_stream = None
+        self._graph_warned = False
 
     # ---- nn.Module look-alikes (inference.py:27-28) -------------------------------------------------
     def eval(self):
         return self
 
     def to(self, device):
-        if self._hs and torch.device(device) != self._device:
+        if self._h is not None and torch.device(device) != self._device:
             raise _lib.ArtalkError("weights already live on %s" % self._device)
         self._device = torch.device(device)
         return self
@@ -111,36 +110,42 @@ class BitwiseARModel:
     def device(self):
         return self._device
 
+    def _call(self, fn, *args):
+        """One C-ABI call with this model's device current (the library allocates / launches on the current device)."""
+        with torch.cuda.device(self._device):
+            _lib.check(fn(*args))
+
     def load_state_dict(self, state_dict, strict=True):
         if not strict:
             raise ValueError("only strict loading is supported (inference.py:28)")
         dev = _lib.require_cuda(self._device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self._device = dev
         lib = _lib.lib()
         self.close()
         with torch.cuda.device(dev):
             self._tensors = repack(state_dict, self.cfg, dev, self.precision)
             ccfg = _lib.make_config(self.cfg, self.precision)
             code = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.int32: _lib.I32}
-            for _ in range(self.lanes):            # every lane shares the weight tensors, owns workspace + graphs
-                h = C.c_void_p()
-                _lib.check(lib.artalk_create(C.byref(ccfg), C.byref(h)))
-                self._hs.append(h)
-                for name, t in self._tensors.items():
-                    _lib.check(lib.artalk_set_tensor(h, name.encode(), t.data_ptr(), code[t.dtype], t.numel()))
-                _lib.check(lib.artalk_finalize(h))
-                if self.latency_rows:
-                    _lib.check(lib.artalk_set_latency_mode(h, self.latency_rows))
-            self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
+            h = C.c_void_p()
+            _lib.check(lib.artalk_create(C.byref(ccfg), C.byref(h)))
+            self._h = h
+            for name, t in self._tensors.items():
+                _lib.check(lib.artalk_set_tensor(h, name.encode(), t.data_ptr(), code[t.dtype], t.numel()))
+            _lib.check(lib.artalk_finalize(h))
+            if self.latency_rows:
+                _lib.check(lib.artalk_set_latency_mode(h, self.latency_rows))
             torch.cuda.synchronize(dev)
         self._init_words = None
         return self
 
     def close(self):
-        if self._hs:
-            torch.cuda.synchronize(self._device)
-            for h in self._hs:
-                _lib.lib().artalk_destroy(h)
-        self._hs, self._streams, self._tensors = [], [], {}
+        if self._h is not None:
+            with torch.cuda.device(self._device):
+                torch.cuda.synchronize(self._device)
+                _lib.lib().artalk_destroy(self._h)
+        self._h, self._tensors = None, {}
 
     def __del__(self):
         try:
@@ -149,41 +154,49 @@ class BitwiseARModel:
             pass
 
     def set_workspace_limit(self, n_bytes: int):
-        for lane in range(len(self._hs)):
-            _lib.check(_lib.lib().artalk_set_workspace_limit(self._handle(lane), n_bytes))
+        self._call(_lib.lib().artalk_set_workspace_limit, self._handle(), n_bytes)
 
     def set_latency_mode(self, on=True, max_rows: int = 128):
         """Batch-1 / few-clip streaming: GEMMs with at most ``max_rows`` rows take the latency kernel (include/artalk_b200.h,
         artalk_set_latency_mode). Off (default) = throughput mode, whose arithmetic does not depend on the batch size."""
         self.latency_rows = int(max_rows) if on else 0
-        for lane in range(len(self._hs)):
-            _lib.check(_lib.lib().artalk_set_latency_mode(self._handle(lane), self.latency_rows))
+        if self._h is not None:
+            self._call(_lib.lib().artalk_set_latency_mode, self._handle(), self.latency_rows)
 
     def enable_graphs(self, on: bool = True):
-        for lane in range(len(self._hs)):
-            _lib.check(_lib.lib().artalk_enable_graphs(self._handle(lane), int(on)))
+        self._call(_lib.lib().artalk_enable_graphs, self._handle(), int(on))
 
-    def _handle(self, lane: int = 0):
-        if not self._hs:
+    def graph_status(self):
+        """(graphs instantiated, replays so far, failure text or None): a failed capture makes the engine launch eagerly."""
+        n, r = C.c_int(0), C.c_int(0)
+        rc = _lib.lib().artalk_graph_status(self._handle(), C.byref(n), C.byref(r))
+        msg = None
+        if rc != 0:
+            m = _lib.lib().artalk_last_error()
+            msg = m.decode() if m else "unknown"
+        return n.value, r.value, msg
+
+    def _handle(self):
+        if self._h is None:
             raise _lib.ArtalkError("no weights loaded: call load_state_dict first")
-        return self._hs[lane]
+        return self._h
 
     # ---- stage-level calls (each is one C-ABI call on the current stream) ------------------------------
     def _dev(self, t, dtype=torch.float32):
         pinned = t.device.type == "cpu" and t.is_pinned()
         return t.to(self._device, dtype, non_blocking=pinned).contiguous()
 
-    def audio_cond(self, chunks: torch.Tensor, lane: int = 0) -> torch.Tensor:
+    def audio_cond(self, chunks: torch.Tensor) -> torch.Tensor:
         """(N, 64000) audio chunks -> (N, 181, 1024) conditioning (wav2vec2 + area pooling)."""
         x = self._dev(chunks)
         if x.dim() != 2 or x.shape[1] != self.cfg.chunk_samples:
             raise ValueError("expected (N, %d) chunks, got %s" % (self.cfg.chunk_samples, tuple(x.shape)))
         cond = torch.empty(x.shape[0], self.cfg.seq_tokens, self.cfg.cond_dim, device=self._device)
-        _lib.check(_lib.lib().artalk_audio_encode(self._handle(lane), x.data_ptr(), x.shape[0], cond.data_ptr(),
-                                                  _lib.stream_ptr(self._device)))
+        self._call(_lib.lib().artalk_audio_encode, self._handle(), x.data_ptr(), x.shape[0], cond.data_ptr(),
+                   _lib.stream_ptr(self._device))
         return cond
 
-    def style_cond(self, style_motion: Optional[torch.Tensor], batch: int, lane: int = 0) -> torch.Tensor:
+    def style_cond(self, style_motion: Optional[torch.Tensor], batch: int) -> torch.Tensor:
         """(B,50,106) or None -> (B,768) style token (app/models.py:67-73)."""
         if style_motion is None:
             return self._tensors["style.null"][None].expand(batch, -1).contiguous()
@@ -191,21 +204,21 @@ class BitwiseARModel:
         if s.dim() != 3 or s.shape[0] != batch or s.shape[1] != self.cfg.style_len or s.shape[2] != self.cfg.motion_dim:
             raise ValueError("style_motion must be (%d, %d, %d), got %s" % (batch, self.cfg.style_len, self.cfg.motion_dim, tuple(s.shape)))
         out = torch.empty(batch, self.cfg.embed_dim, device=self._device)
-        _lib.check(_lib.lib().artalk_style_encode(self._handle(lane), s.data_ptr(), batch, out.data_ptr(), _lib.stream_ptr(self._device)))
+        self._call(_lib.lib().artalk_style_encode, self._handle(), s.data_ptr(), batch, out.data_ptr(), _lib.stream_ptr(self._device))
         return out
 
-    def motion_to_words(self, motion: torch.Tensor, enc_out: Optional[torch.Tensor] = None, lane: int = 0) -> torch.Tensor:
+    def motion_to_words(self, motion: torch.Tensor, enc_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         m = self._dev(motion)
         words = torch.empty(m.shape[0], self.cfg.seq_tokens, dtype=torch.int32, device=self._device)
-        _lib.check(_lib.lib().artalk_motion_to_bits(self._handle(lane), m.data_ptr(), m.shape[0], words.data_ptr(), _lib.ptr(enc_out),
-                                                    _lib.stream_ptr(self._device)))
+        self._call(_lib.lib().artalk_motion_to_bits, self._handle(), m.data_ptr(), m.shape[0], words.data_ptr(), _lib.ptr(enc_out),
+                   _lib.stream_ptr(self._device))
         return words
 
-    def words_to_motion(self, prev_words: torch.Tensor, words: torch.Tensor, lane: int = 0) -> torch.Tensor:
+    def words_to_motion(self, prev_words: torch.Tensor, words: torch.Tensor) -> torch.Tensor:
         pw, w = self._dev(prev_words, torch.int32), self._dev(words, torch.int32)
         out = torch.empty(w.shape[0], self.cfg.chunk_frames, self.cfg.motion_dim, device=self._device)
-        _lib.check(_lib.lib().artalk_bits_to_motion(self._handle(lane), pw.data_ptr(), w.data_ptr(), w.shape[0], out.data_ptr(),
-                                                    _lib.stream_ptr(self._device)))
+        self._call(_lib.lib().artalk_bits_to_motion, self._handle(), pw.data_ptr(), w.data_ptr(), w.shape[0], out.data_ptr(),
+                   _lib.stream_ptr(self._device))
         return out
 
     def initial_words(self, batch: int) -> torch.Tensor:
@@ -217,24 +230,24 @@ class BitwiseARModel:
         return self._init_words.repeat(batch, 1)          # fresh copy: ar_chunk updates prev_words in place
 
     def ar_chunk(self, cond: torch.Tensor, style: torch.Tensor, prev_words: torch.Tensor, motion_out: torch.Tensor,
-                 words_out=None, logits_out=None, forced_words=None, enc_out=None, lane: int = 0):
+                 words_out=None, logits_out=None, forced_words=None, enc_out=None):
         """One chunk for all clips; ``cond`` is (B,181,1024) possibly a strided view over clips; prev_words updated in place."""
         B = style.shape[0]
         assert cond.stride(2) == 1 and cond.stride(1) == self.cfg.cond_dim
-        _lib.check(_lib.lib().artalk_ar_chunk(
-            self._handle(lane), B, cond.data_ptr(), cond.stride(0), style.data_ptr(), prev_words.data_ptr(), motion_out.data_ptr(),
-            _lib.ptr(words_out), _lib.ptr(logits_out), _lib.ptr(forced_words), _lib.ptr(enc_out), _lib.stream_ptr(self._device)))
+        self._call(_lib.lib().artalk_ar_chunk,
+                   self._handle(), B, cond.data_ptr(), cond.stride(0), style.data_ptr(), prev_words.data_ptr(), motion_out.data_ptr(),
+                   _lib.ptr(words_out), _lib.ptr(logits_out), _lib.ptr(forced_words), _lib.ptr(enc_out), _lib.stream_ptr(self._device))
 
     # ---- app/models.py:62-121 -------------------------------------------------------------------------
-    def _run_clips(self, audio, style_motion, motion, b0, b1, lane, trace, teacher_words, teacher_prev_words, audio_ready=None):
-        """Full pipeline for clips [b0, b1) on the current stream with lane ``lane``'s engine; writes motion[b0:b1]."""
+    def _run_clips(self, audio, style_motion, motion, b0, b1, trace, teacher_words, teacher_prev_words, audio_ready=None):
+        """Full pipeline for clips [b0, b1) on the current stream; writes motion[b0:b1]."""
         cfg = self.cfg
         T, n_chunks = cfg.chunk_frames, motion.shape[1]
         nb = b1 - b0
-        style = self.style_cond(None if style_motion is None else style_motion[b0:b1], nb, lane)
+        style = self.style_cond(None if style_motion is None else style_motion[b0:b1], nb)
         if audio_ready is not None:                       # audio upload in flight on the copy stream (see inference)
             torch.cuda.current_stream(self._device).wait_event(audio_ready)
-        cond = self.audio_cond(audio[b0:b1].reshape(nb * n_chunks, cfg.chunk_samples), lane).view(
+        cond = self.audio_cond(audio[b0:b1].reshape(nb * n_chunks, cfg.chunk_samples)).view(
             nb, n_chunks, cfg.seq_tokens, cfg.cond_dim)
         if trace is not None:
             trace["cond"][b0:b1].copy_(cond); trace["style"][b0:b1].copy_(style)
@@ -254,7 +267,7 @@ class BitwiseARModel:
                     forced = teacher_words[b0 + g0:b0 + g1, c].to(self._device, torch.int32).contiguous()
                 self.ar_chunk(cond[g0:g1, c], style[g0:g1], prev_words, chunk_out,
                               words_out=None if tr is None else tr["words"], logits_out=None if tr is None else tr["logits"],
-                              forced_words=forced, enc_out=None if tr is None else tr["enc"], lane=lane)
+                              forced_words=forced, enc_out=None if tr is None else tr["enc"])
                 motion[b0 + g0:b0 + g1, c].copy_(chunk_out)
                 if tr is not None:
                     s = slice(b0 + g0, b0 + g1)
@@ -311,27 +324,14 @@ class BitwiseARModel:
                          words=torch.empty(B, n_chunks, cfg.seq_tokens, dtype=torch.int32, device=self._device),
                          prev_words=torch.empty(B, n_chunks, cfg.seq_tokens, dtype=torch.int32, device=self._device),
                          enc_out=torch.empty(B, n_chunks, T, cfg.code_dim, device=self._device))
-        n_lanes = min(self.lanes, max(1, B // max(1, self.min_lane_clips)))
-        if n_lanes <= 1:
-            self._run_clips(audio, style_motion, motion, 0, B, 0, trace, teacher_words, teacher_prev_words, audio_ready)
-        else:
-            self.initial_words(1)                       # cached before the lanes fork
-            main = torch.cuda.current_stream(self._device)
-            fork = torch.cuda.Event()
-            fork.record(main)
-            bounds = [(B * i) // n_lanes for i in range(n_lanes + 1)]
-            for lane in range(n_lanes):
-                s = self._streams[lane]
-                s.wait_event(fork)
-                with torch.cuda.stream(s):
-                    self._run_clips(audio, style_motion, motion, bounds[lane], bounds[lane + 1], lane, trace, teacher_words,
-                                    teacher_prev_words, audio_ready)
-                    for t in (audio, motion, style_motion) + (tuple(trace.values()) if trace is not None else ()):
-                        if isinstance(t, torch.Tensor):
-                            t.record_stream(s)
-                join = torch.cuda.Event()
-                join.record(s)
-                main.wait_event(join)
+        with torch.cuda.device(self._device):
+            self._run_clips(audio, style_motion, motion, 0, B, trace, teacher_words, teacher_prev_words, audio_ready)
+        if not self._graph_warned:
+            _, _, failure = self.graph_status()
+            if failure:
+                import warnings
+                warnings.warn("artalk_b200: %s — the chunk body is launched eagerly (slower)" % failure, RuntimeWarning)
+                self._graph_warned = True
         pred_motions = motion.view(B, n_chunks * T, cfg.motion_dim)[:, :seq_length]
         if with_gtmotion:
             min_length = min(batch["motion"].shape[1], pred_motions.shape[1])

@@ -65,6 +65,59 @@ def gather_motion(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor
     return torch.cat(parts, dim=0)
 
 
+class MotionGather:
+    """The path's one collective, off the compute stream: ``start`` enqueues the all-gather of a step's motion on a side
+    stream (it waits for the producer through an event), so the collective of step i overlaps the compute of step i+1;
+    ``wait`` makes the current stream wait for it and returns the gathered tensor. CUDA events around the collective give
+    its device time (``gather_ms``). Falls back to a synchronous gather on CPU process groups (gloo tests)."""
+
+    def __init__(self, device=None):
+        self.device = torch.device(device) if device is not None else None
+        self.cuda = self.device is not None and self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self._pending = []
+        self.times_ms = []
+
+    def start(self, local: torch.Tensor, n_total: int, group=None):
+        if not self.cuda:
+            h = {"out": gather_motion(local, n_total, group), "done": None}
+            self._pending.append(h)
+            return h
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            t0.record(self.stream)
+            out = gather_motion(local, n_total, group)
+            t1.record(self.stream)
+        local.record_stream(self.stream)
+        h = {"out": out, "done": t1, "t0": t0}
+        self._pending.append(h)
+        return h
+
+    def wait(self, h=None):
+        """Current stream waits for ``h`` (default: every pending gather); returns the gathered motion of ``h`` / the last one."""
+        hs = [h] if h is not None else list(self._pending)
+        out = None
+        for x in hs:
+            if x["done"] is not None:
+                torch.cuda.current_stream(self.device).wait_event(x["done"])
+                x["out"].record_stream(torch.cuda.current_stream(self.device))
+            out = x["out"]
+            if x in self._pending:
+                self._pending.remove(x)
+                if x["done"] is not None:
+                    self.times_ms.append((x["t0"], x["done"]))
+        return out
+
+    def mean_ms(self) -> float:
+        """Mean device time of the completed gathers (call after a synchronize)."""
+        if not self.times_ms:
+            return 0.0
+        return sum(a.elapsed_time(b) for a, b in self.times_ms) / len(self.times_ms)
+
+
 def sharded_inference(engine, make_audio, make_style, n_clips: int, clip_length=None) -> torch.Tensor:
     """Run ``engine.inference_batch`` on this rank's shard and gather: ``make_audio(lo, hi)`` / ``make_style(lo, hi)``
     produce the shard's inputs (so a large job is never materialised on one host). Returns ``(n_clips, T, 106)``."""

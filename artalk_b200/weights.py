@@ -79,7 +79,7 @@ def savgol_hat(window: int, poly: int) -> np.ndarray:
 def repack(sd: Dict[str, torch.Tensor], cfg: ModelConfig, device, precision: str) -> Dict[str, torch.Tensor]:
     """reference state_dict -> {canonical name: contiguous device tensor}."""
     validate_state_dict(sd, cfg)
-    wt = torch.float32 if precision == "fp32" else torch.bfloat16
+    wt = torch.bfloat16 if precision == "bf16" else torch.float32       # "bf16x3" / "bf16x6": the engine splits fp32 weights itself
     f32 = torch.float32
     g = lambda k: sd[k].detach().to("cpu", f32)
     out: Dict[str, torch.Tensor] = {}

@@ -8,8 +8,11 @@
  * Conventions: plain pointers and sizes, no C++/torch types; every pointer is a DEVICE pointer unless named host_*;
  * tensors are dense row-major; `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are
  * asynchronous on that stream; return value 0 = ok, otherwise an ARTALK_E* code with text in artalk_last_error().
- * An engine is not thread-safe; different engines may be used concurrently. Tensor memory handed to
- * artalk_set_tensor stays owned by the caller and must outlive the engine.
+ * An engine is not thread-safe; different engines (also on different devices of one process) may be used concurrently:
+ * per-device state is kept per device ordinal and the launch counter is atomic. Every call must be made with the engine's
+ * device current (cudaSetDevice / torch.cuda.device), as for any CUDA library that takes a stream. artalk_set_option /
+ * artalk_enable_pdl are process-wide developer switches: set them while no other thread is launching. Tensor memory handed
+ * to artalk_set_tensor stays owned by the caller and must outlive the engine.
  */
 #ifndef ARTALK_B200_H
 #define ARTALK_B200_H
@@ -34,6 +37,11 @@ extern "C" {
 
 #define ARTALK_PRECISION_FP32 0 /* CUDA-core fp32 GEMMs; parity tolerance 1e-3 */
 #define ARTALK_PRECISION_BF16 1 /* tcgen05 bf16 GEMMs, fp32 accumulate; parity tolerance 2e-2 */
+/* parity-grade tensor-core modes: fp32 data flow (weights handed over in fp32), every GEMM operand split into 2 / 3 bf16
+ * pieces and multiplied on the tcgen05 pipe in 3 / 6 passes with fp32 accumulation; attention, norms and activations in fp32.
+ * Same tolerance contract as FP32 (bits exact where the logit margin > 1e-3, motion / vertices within 1e-3). */
+#define ARTALK_PRECISION_BF16X3 2
+#define ARTALK_PRECISION_BF16X6 3
 
 typedef struct artalk_engine artalk_engine_t;
 
@@ -69,6 +77,10 @@ size_t artalk_workspace_bytes(const artalk_engine_t* e);
 /* the body of artalk_ar_chunk is replayed from a CUDA graph after one eager warm-up per (n_clips, teacher forcing);
  * enable = 0 drops the graphs and launches eagerly (default: enabled) */
 int artalk_enable_graphs(artalk_engine_t* e, int enable);
+/* graphs currently instantiated / replays so far (either pointer may be NULL). Returns ARTALK_ESTATE, with the reason in
+ * artalk_last_error(), if a capture or instantiation failed and the engine fell back to eager launches (it also says so once
+ * on stderr); artalk_enable_graphs(e, 1) re-arms capture. */
+int artalk_graph_status(const artalk_engine_t* e, int* n_graphs, int* n_replays);
 /* latency mode for batch-1 / few-clip streaming (BASELINE configs[4]; the reference's per-chunk loop, app/models.py:76-115,
  * run one chunk at a time): max_rows > 0 sends every bf16 GEMM of this engine with at most max_rows rows (and a small output)
  * to the latency kernel (skinny.cu: 64-row tiles, ~100 CTAs streaming disjoint weight slices) instead of the 128-row tcgen05
@@ -150,9 +162,9 @@ int artalk_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_i
 /* --- measurement hooks (bench.py) ---
  * artalk_launch_count: kernels launched by this library in this process so far.
  * artalk_profile_enable(e, 1): bracket every GEMM / attention launch of the engine with CUDA events on the launching
- * stream; artalk_profile_read synchronises and fills host_out8[12] (12 doubles; [6..8] = launches, total ms and flops per
- * launch of the GEMM shape with the largest summed duration) = {gemm launches, gemm ms, gemm flops, attention
- * launches, attention ms, attention flops, 0, 0} accumulated since the last enable call. */
+ * stream; artalk_profile_read synchronises and fills host_out16[16] (16 doubles) = {gemm launches, gemm ms, gemm flops,
+ * attention launches, attention ms, attention flops, then the GEMM shape with the largest summed duration: launches, total
+ * ms, flops per launch, M, N, K, 0...} accumulated since the last enable call. */
 unsigned long long artalk_launch_count(void);
 /* programmatic dependent launch (default on): kernels are launched with the programmatic-stream-serialization attribute so
  * a kernel's prologue (barrier init, TMEM allocation, weight prefetch) overlaps the tail of its predecessor; 0 = plain
@@ -167,7 +179,7 @@ int artalk_set_option(const char* name, int value);
 int artalk_trace_begin(void* stream);
 long artalk_trace_end(char* host_buf, long cap, void* stream);
 int artalk_profile_enable(artalk_engine_t* e, int enable);
-int artalk_profile_read(artalk_engine_t* e, double* host_out8, void* stream);
+int artalk_profile_read(artalk_engine_t* e, double* host_out16, void* stream);
 
 /* ---------------- operator-level entry points (unit parity tests of single kernels) ---------------- */
 typedef struct artalk_rowmap { int rpb; int64_t bs, rs; } artalk_rowmap_t;
@@ -182,9 +194,15 @@ typedef struct artalk_gemm {
   const void* gate; int gate_dt; artalk_rowmap_t gate_map;
   const float* resid; artalk_rowmap_t resid_map;
   float* out32; void* out_act; int out_act_dt; artalk_rowmap_t c_map;
+  int tap_slots;                 /* bf16 kernel, tap mode on piece blocks: slots per 64-column block (0 / 1 = plain operands) */
+  int exact;                     /* bf16 kernel: 1 = libm-accurate activations (parity-grade mode) */
 } artalk_gemm_t;
 /* out = resid + gate * act(A W^T + bias); precision selects the fp32 CUDA-core or the bf16 tcgen05 kernel */
 int artalk_op_gemm(const artalk_gemm_t* g, int precision, void* stream);
+/* operand splitting of the parity-grade modes: x [n] f32 -> out [n / 64][slots][64] bf16 piece blocks (slots = 3 or 6; n a
+ * multiple of 64; is_w selects the weight-side slot order). A bf16 artalk_op_gemm on split A and W with K' = slots * K (row
+ * strides multiplied alike) then computes A W^T to ~2^-17 (3) / ~2^-24 (6) relative per product. */
+int artalk_op_split_bf16(const float* x, void* out, int64_t n, int slots, int is_w, void* stream);
 
 typedef struct artalk_attn {
   const void* q; const void* k; const void* v; void* out;

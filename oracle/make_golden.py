@@ -125,8 +125,25 @@ def run_case(case, report):
     return sd, ref
 
 
-def run_engine_case(report):
-    """ARTAvatarInferEngine.inference incl. savgol + zeroing (inference.py:47-57) on TINY."""
+def write_eng1_audio():
+    """demo/eng1.wav exactly as the reference's CLI feeds it (inference.py:229-231): torchaudio.load is unusable here (needs
+    torchcodec), so the PCM is read with the stdlib and scaled like torchaudio does (int16 / 32768), then
+    ``torchaudio.transforms.Resample(sr, 16000)(audio).mean(dim=0)``."""
+    import wave
+    import torchaudio
+    w = wave.open(os.path.join(live.REF_ROOT, "demo", "eng1.wav"))
+    assert w.getsampwidth() == 2
+    pcm = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).reshape(-1, w.getnchannels()).T
+    audio = torch.from_numpy(pcm.astype(np.float32) / 32768.0)
+    audio = torchaudio.transforms.Resample(w.getframerate(), 16000)(audio).mean(dim=0)
+    np.savez_compressed(os.path.join(GOLD, "eng1_audio.npz"), audio=audio[None].numpy())
+    print("eng1_audio", tuple(audio.shape))
+
+
+def run_engine_case(report, name="tiny_style", clip_length=120):
+    """ARTAvatarInferEngine.inference incl. savgol + zeroing (inference.py:47-57)."""
+    if name != "tiny_style":
+        return run_engine_case_named(report, name, clip_length)
     case = CASES["tiny_style"]
     cfg = case.cfg
     sd = synthetic.make_state_dict(cfg, case.weight_seed)
@@ -147,6 +164,23 @@ def run_engine_case(report):
     ov = get_flame_verts(asset, shape_code, out, with_global=True)
     report["engine_tiny"]["verts_maxabs"] = float((ov - verts).abs().max())
     np.savez_compressed(os.path.join(GOLD, "engine_tiny_verts.npz"), verts=verts[:3].numpy())
+
+
+def run_engine_case_named(report, name, clip_length):
+    case = CASES[name]
+    cfg = case.cfg
+    sd = synthetic.make_state_dict(cfg, case.weight_seed)
+    asset = synthetic.make_flame_asset(0)
+    eng = live.load_engine(cfg, sd, asset, clip_length=clip_length)
+    eng.set_style_motion(case.style()[0])
+    audio = case.audio()[0]
+    out = eng.inference(audio)
+    orc = Oracle(sd, cfg)
+    with torch.no_grad():
+        o = orc.engine_inference(audio, case.style()[0:1], clip_length=clip_length)
+    np.savez_compressed(os.path.join(GOLD, "engine_%s.npz" % name), motion=out.numpy())
+    report["engine_" + name] = {"maxabs": float((o - out).abs().max()), "shape": list(out.shape)}
+    print("engine_" + name, report["engine_" + name])
 
 
 def run_flame(report):
@@ -177,12 +211,16 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     report = {"torch": torch.__version__, "reference": live.REF_ROOT}
     only = sys.argv[1:]
+    if not only or "eng1_audio" in only or not os.path.exists(os.path.join(GOLD, "eng1_audio.npz")):
+        write_eng1_audio()
     for name, case in CASES.items():
         if only and name not in only:
             continue
         run_case(case, report)
     if not only or "engine" in only:
         run_engine_case(report)
+    if not only or "engine_full_eng1" in only:
+        run_engine_case(report, "full_eng1", 750)
     if not only or "flame" in only:
         run_flame(report)
     path = os.path.join(GOLD, "PIN_REPORT.json")

@@ -35,7 +35,11 @@ def _stub_modules():
 
     def mk(name):
         m = types.ModuleType(name)
-        m.__getattr__ = lambda n: _Any          # type: ignore[attr-defined]
+        def _ga(n):
+            if n.startswith("__"):                 # inspect / importlib probe __file__, __spec__ ...: behave like a plain module
+                raise AttributeError(n)
+            return _Any
+        m.__getattr__ = _ga                      # type: ignore[attr-defined]
         m.__path__ = []                          # behave like a package
         sys.modules.setdefault(name, m)
     for n in ("gradio", "gtts", "av", "pytorch3d", "pytorch3d.io", "pytorch3d.structures",

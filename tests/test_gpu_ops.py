@@ -21,8 +21,9 @@ def rowmap(rpb=0, bs=0, rs=0):
 
 def run_gemm(precision, A, W, M, N, K, *, a_map=None, bias=None, act=0, gate=None, gate_map=None, resid=None,
              resid_map=None, out32=None, out_act=None, c_map=None, tap_w=0, tap_pad=0, groups=1, a_gs=0, w_gs=0, c_gs=0,
-             bias_gs=0, ldw=None):
+             bias_gs=0, ldw=None, tap_slots=0, exact=0):
     g = _lib.Gemm()
+    g.tap_slots, g.exact = tap_slots, exact
     g.A, g.W = A.data_ptr(), W.data_ptr()
     g.a_map = a_map or rowmap(0, 0, K)
     g.ldw = ldw if ldw is not None else K
@@ -268,6 +269,92 @@ def test_pos_conv_grouped_tap_gemm(pname, prec, dt, tol):
     assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
+# ----------------------------------------------------------------------------- parity-grade tensor-core mode (split.cu)
+def split_op(x, slots, is_w):
+    """fp32 tensor -> bf16 piece blocks [numel / 64][slots][64] through artalk_op_split_bf16."""
+    x = x.contiguous()
+    out = torch.empty(x.numel() * slots, device=dev(), dtype=torch.bfloat16)
+    _lib.check(_lib.lib().artalk_op_split_bf16(x.data_ptr(), out.data_ptr(), x.numel(), slots, int(is_w), _lib.stream_ptr(dev())))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("slots", [3, 6])
+def test_split_pieces_reconstruct_operand(slots):
+    """The piece blocks hold p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1) in the slot order A: 0 1 0 | 1 2 0,
+    W: 0 0 1 | 1 0 2, and the pieces sum back to x to 2^-17 (2 pieces) / 2^-24 (3 pieces) relative."""
+    g = torch.Generator(device="cpu").manual_seed(slots)
+    x = (torch.randn(3 * 64 * 5, generator=g) * torch.logspace(-3, 3, 960)).to(dev())
+    p0 = x.to(torch.bfloat16).float()
+    p1 = (x - p0).to(torch.bfloat16).float()
+    p2 = (x - p0 - p1).to(torch.bfloat16).float()
+    pieces = [p0, p1, p2]
+    order = {(3, 0): [0, 1, 0], (3, 1): [0, 0, 1], (6, 0): [0, 1, 0, 1, 2, 0], (6, 1): [0, 0, 1, 1, 0, 2]}
+    for is_w in (0, 1):
+        got = split_op(x, slots, is_w).float().view(-1, slots, 64)
+        for s_, pc in enumerate(order[(slots, is_w)]):
+            assert torch.equal(got[:, s_], pieces[pc].view(-1, 64)), (slots, is_w, s_)
+    n_p = 2 if slots == 3 else 3
+    rel = ((sum(pieces[:n_p]) - x).abs() / x.abs().clamp_min(1e-30)).max().item()
+    assert rel < (2.0 ** -16 if slots == 3 else 2.0 ** -23), rel
+
+
+@pytest.mark.parametrize("slots,tol", [(3, 3e-5), (6, 1.5e-6)])
+@pytest.mark.parametrize("M,N,K,act", [(300, 768, 768, 0), (129, 1024, 4096, 1), (1, 64, 768, 0), (9700, 2048, 512, 2),
+                                       (200, 106, 512, 0), (38000, 1024, 1024, 0)])
+def test_split_gemm_is_fp32_grade(slots, tol, M, N, K, act):
+    """The UNCHANGED bf16 tcgen05 kernels (1-CTA and CTA-pair) on piece blocks with K' = slots * K reproduce the fp64 product
+    of the fp32 operands: ~2^-17 relative per product with 2 pieces (3 passes), fp32 grade with 3 pieces (6 passes), measured
+    against sum_k |a_k||w_k| (the scale rounding errors live on). exact = 1: libm-accurate GELU in the epilogue."""
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N + slots)
+    A = torch.randn(M, K, generator=g).to(dev())
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev())
+    b = torch.randn(N, generator=g).to(dev())
+    As, Ws = split_op(A, slots, 0), split_op(W, slots, 1)
+    out = torch.full((M, N), float("nan"), device=dev())
+    run_gemm(1, As, Ws, M, N, slots * K, bias=b, act=act, out32=out, exact=1)
+    pre = A.double() @ W.double().t() + b.double()
+    ref = ACTS[act](pre)
+    mag = (A.double().abs() @ W.double().abs().t()).clamp_min(1.0)           # error scale of a length-K dot product
+    err = ((out.double() - ref).abs() / mag).max().item()
+    assert torch.isfinite(out).all()
+    assert err < tol, err
+
+
+@pytest.mark.parametrize("slots,tol", [(3, 3e-5), (6, 1.5e-6)])
+def test_split_conv_window_and_tap_views(slots, tol):
+    """Piece blocks keep the strided views working: overlapping-row conv windows (every stride x slots) and the grouped tap
+    mode of the positional conv (tap_slots: k-block kb reads slot kb % slots of tap kb / slots)."""
+    # conv k=3, s=2 over channels-last input
+    n, L_in, Cc, k, s = 3, 401, 512, 3, 2
+    L_out = (L_in - k) // s + 1
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(n, L_in, Cc, generator=g).to(dev())
+    w = (torch.randn(Cc, Cc, k, generator=g) / math.sqrt(Cc * k)).to(dev())
+    b = torch.randn(Cc, generator=g).to(dev())
+    wp = w.permute(0, 2, 1).reshape(Cc, k * Cc).contiguous()
+    out = torch.empty(n * L_out, Cc, device=dev())
+    S = slots
+    run_gemm(1, split_op(x, S, 0), split_op(wp, S, 1), n * L_out, Cc, S * k * Cc, a_map=rowmap(L_out, S * L_in * Cc, S * s * Cc),
+             bias=b, out32=out, exact=1)
+    ref = F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), stride=s).transpose(1, 2).reshape(n * L_out, Cc)
+    assert ((out.double() - ref).abs().max().item()) < tol * 40
+    # positional conv: grouped, k=128, pad 64, GELU + residual
+    n, Fr, H, G, K = 2, 199, 1024, 16, 128
+    gw = H // G
+    h = torch.randn(n, Fr, H, generator=g).to(dev())
+    w = (torch.randn(H, gw, K, generator=g) / math.sqrt(gw * K)).to(dev())
+    b = torch.randn(H, generator=g).to(dev())
+    wp = w.view(G, gw, gw, K).permute(0, 1, 3, 2).reshape(G, gw, K * gw).contiguous()
+    out = torch.empty(n * Fr, H, device=dev())
+    run_gemm(1, split_op(h, S, 0), split_op(wp, S, 1), n * Fr, gw, S * K * gw, a_map=rowmap(Fr, S * Fr * H, S * H), tap_w=gw,
+             tap_pad=K // 2, groups=G, a_gs=gw, w_gs=S * gw * K * gw, c_gs=gw, bias_gs=gw, bias=b, act=1, resid=h.view(-1, H),
+             resid_map=rowmap(0, 0, H), out32=out, c_map=rowmap(0, 0, H), ldw=S * K * gw, tap_slots=S, exact=1)
+    pc = F.conv1d(h.double().transpose(1, 2), w.double(), b.double(), padding=K // 2, groups=G)[:, :, :-1]
+    ref = h.double() + F.gelu(pc).transpose(1, 2)
+    assert (out.double() - ref.reshape(n * Fr, H)).abs().max().item() < tol * 40
+
+
 def run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, scale, split=0):
     a = _lib.Attn()
     a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
@@ -291,15 +378,9 @@ def test_attention(dt, tol, n_seq, H, D, lq, lk, split):
     v = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), dt)
     out = torch.empty(n_seq, lq, Cw, device=dev(), dtype=dt)
     scale = 0.3
-    few = dt == torch.bfloat16 and lq <= 8 and D == 64          # also through the opt-in few-query kernel (skinny.cu)
-    for few_on in ((8, 0) if few else (0,)):
-        _lib.check(_lib.lib().artalk_set_option(b"attn_few_max_lq", few_on))
-        try:
-            out.fill_(float("nan"))
-            run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), scale, split)
-        finally:
-            _lib.check(_lib.lib().artalk_set_option(b"attn_few_max_lq", 0))
-        _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol)
+    out.fill_(float("nan"))
+    run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), scale, split)
+    _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol)
 
 
 def _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol):

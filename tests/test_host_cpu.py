@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol():
     l = _lib.lib()                                  # raises if the .so is missing (no fallback)
     for name in declared:
         assert hasattr(l, name), name
-    assert l.artalk_abi_version() == 1
+    assert l.artalk_abi_version() == 2
 
 
 def test_no_cpu_fallback():

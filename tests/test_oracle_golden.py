@@ -25,7 +25,7 @@ def test_wire_format_key_count():
             assert v["bit_mismatch_margin_gt_1e-3"] == 0, k
 
 
-@pytest.mark.parametrize("name", ["tiny_style", "tiny_null", "tiny_ragged", "full_10s"])
+@pytest.mark.parametrize("name", ["tiny_style", "tiny_null", "tiny_ragged", "full_10s", "full_eng1", "full_30s"])
 def test_oracle_matches_reference_golden(name):
     case = CASES[name]
     g = gu.load(name)
@@ -56,13 +56,17 @@ def test_oracle_matches_reference_golden(name):
     assert (pb != gpb).float().mean() < 2e-3
 
 
-def test_engine_level_golden():
-    case = CASES["tiny_style"]
-    g = gu.load("engine_tiny")
+@pytest.mark.parametrize("name,fixture,clip_length,frames", [("tiny_style", "engine_tiny", 120, 120),
+                                                             ("full_eng1", "engine_full_eng1", 750, 340)])
+def test_engine_level_golden(name, fixture, clip_length, frames):
+    """ARTAvatarInferEngine.inference incl. savgol + clip + zeroing (inference.py:47-57); full_eng1 = BASELINE configs[0]:
+    the reference's demo/eng1.wav (217 088 samples -> 340 frames, 4 chunks), full-depth model."""
+    case = CASES[name]
+    g = gu.load(fixture)
     orc = Oracle(gu.state_dict(case.cfg_name), case.cfg)
     with torch.no_grad():
-        m = orc.engine_inference(case.audio()[0], case.style()[0:1], clip_length=120)
-    assert tuple(m.shape) == (120, 106)
+        m = orc.engine_inference(case.audio()[0], case.style()[0:1], clip_length=clip_length)
+    assert tuple(m.shape) == (frames, 106)
     np.testing.assert_allclose(m.numpy(), g["motion"], atol=2e-4, rtol=0)
     assert float(m[:, 104:].abs().max()) == 0.0                     # inference.py:56
 

@@ -50,6 +50,9 @@ def _worker(rank, world, port, n_clips, q):
         out = parallel.sharded_inference(_FakeEngine(), make_audio, make_style, n_clips)
         lo, hi = parallel.shard_bounds(n_clips, world, rank)
         raw = parallel.gather_motion(torch.full((hi - lo, 2, 3), float(rank)), n_clips)
+        mg = parallel.MotionGather(None)                         # CPU group: synchronous fallback of the side-stream gather
+        h = mg.start(torch.full((hi - lo, 2, 3), float(rank)), n_clips)
+        assert torch.equal(mg.wait(h), raw) and mg.mean_ms() == 0.0 and not mg._pending
         q.put((rank, out[:, 0, 0].tolist(), tuple(out.shape), raw[:, 0, 0].tolist()))
         dist.barrier()
     finally:

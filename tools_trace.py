@@ -16,7 +16,6 @@ dev = "cuda:0"
 eng = ARTAvatarInferEngine(load_gaga=False, device=dev, precision=a.precision, state_dict=synthetic.make_state_dict(cfg, 0),
                            config=cfg.to_reference_json(), flame_asset=synthetic.make_flame_asset(0), wav2vec=cfg.wav2vec,
                            make_output_dir=False)
-eng.ARTalk.lanes = 1
 audio = synthetic.make_audio(a.clips, int(a.seconds * 16000)).to(dev)
 style = synthetic.make_style_motion(a.clips).to(dev)
 for _ in range(2):
