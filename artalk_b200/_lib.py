@@ -51,7 +51,7 @@ class Gemm(C.Structure):
         ("gate", C.c_void_p), ("gate_dt", C.c_int), ("gate_map", RowMap),
         ("resid", C.c_void_p), ("resid_map", RowMap),
         ("out32", C.c_void_p), ("out_act", C.c_void_p), ("out_act_dt", C.c_int), ("c_map", RowMap),
-        ("tap_slots", C.c_int), ("exact", C.c_int),
+        ("tap_slots", C.c_int), ("exact", C.c_int), ("split_acc", C.c_int),
     ]
 
 
@@ -101,6 +101,7 @@ SYMBOLS = {
     "artalk_resample_mono": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_int64, C.c_void_p]),
     "artalk_ema_scan": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "artalk_vertex_normals": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "artalk_launch_count": (C.c_ulonglong, []),
     "artalk_enable_pdl": (C.c_int, [C.c_int]),
     "artalk_set_option": (C.c_int, [C.c_char_p, C.c_int]),
@@ -149,8 +150,6 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"attn_simt_max_lq", int(os.environ["ARTALK_ATTN_SIMT_MAX_LQ"]))
         if os.environ.get("ARTALK_SKINNY_MAX_M"):         # 0: the latency-path kernels (skinny.cu) are never taken
             l.artalk_set_option(b"skinny_max_m", int(os.environ["ARTALK_SKINNY_MAX_M"]))
-        if os.environ.get("ARTALK_FLAME_V2"):             # opt-in packed-pair FLAME skinning epilogue (flame_tc.cu)
-            l.artalk_set_option(b"flame_v2", int(os.environ["ARTALK_FLAME_V2"]))
         if os.environ.get("ARTALK_SKINNY_TOKENS"):
             l.artalk_set_option(b"skinny_tokens", int(os.environ["ARTALK_SKINNY_TOKENS"]))
         if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":

@@ -170,6 +170,11 @@ int artalk_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_i
   return launch_ema_scan(points, frame_stride, idx, n_idx, n_frames, state, has_state, keep, (cudaStream_t)stream);
 }
 
+int artalk_vertex_normals(const float* verts, int64_t frame_stride, int n_verts, const int* adj_offsets, const int* adj_pairs,
+                          float* normals, int n_frames, void* stream) {
+  return launch_vertex_normals(verts, frame_stride, n_verts, adj_offsets, adj_pairs, normals, n_frames, (cudaStream_t)stream);
+}
+
 unsigned long long artalk_launch_count(void) { return g_launch_count.load(); }
 int artalk_enable_pdl(int enable) { g_pdl = enable != 0; ++g_option_epoch; return AT_OK; }
 int artalk_set_option(const char* name, int value) {
@@ -185,7 +190,6 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "gemm_band_mb")) { set_gemm_band_mb(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_tma_resid")) { set_gemm_tma_resid(value); return AT_OK; }
   if (!std::strcmp(name, "attn_simt_max_lq")) { set_attn_simt_max_lq(value); return AT_OK; }
-  if (!std::strcmp(name, "flame_v2")) { set_flame_v2(value); return AT_OK; }
   if (!std::strcmp(name, "skinny_tokens")) { g_skinny_tokens = value; return AT_OK; }
   if (!std::strcmp(name, "skinny_max_m")) { set_skinny_max_m(value); return AT_OK; }
   set_last_error("artalk_set_option: unknown option '%s'", name);
@@ -211,7 +215,7 @@ int artalk_op_gemm(const artalk_gemm_t* a, int precision, void* stream) {
   g.bias = a->bias; g.act = a->act; g.gate = a->gate; g.gate_dt = a->gate_dt; g.gate_map = rm(a->gate_map);
   g.resid = a->resid; g.resid_map = rm(a->resid_map); g.out32 = a->out32; g.out_act = a->out_act; g.out_act_dt = a->out_act_dt;
   g.c_map = rm(a->c_map);
-  g.tap_slots = a->tap_slots > 0 ? a->tap_slots : 1; g.exact = a->exact;
+  g.tap_slots = a->tap_slots > 0 ? a->tap_slots : 1; g.exact = a->exact; g.split_acc = a->split_acc;
   g.skinny = g.exact ? 0 : 1;   // op-level calls: any shape within option "skinny_max_m" may take the latency kernel (bf16-grade epilogue)
   return precision == ARTALK_PRECISION_FP32 ? launch_gemm_simt(g, (cudaStream_t)stream) : launch_gemm_tc(g, (cudaStream_t)stream);
 }

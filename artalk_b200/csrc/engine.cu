@@ -221,7 +221,7 @@ int Engine::gemm_split(const GemmArgs& g, cudaStream_t st) {
   GemmArgs h = g;
   h.A = split_buf; h.a_map.rs *= S; h.a_map.bs *= S;
   h.W = it->second; h.ldw *= S; h.w_gs *= S; h.K *= S;
-  h.tap_slots = tap ? S : 1; h.exact = 1; h.skinny = 0;
+  h.tap_slots = tap ? S : 1; h.exact = 1; h.skinny = 0; h.split_acc = S;
   return launch_gemm_tc(h, st);
 }
 

@@ -26,21 +26,6 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + CONST_BYTES + 1024
 static_assert(SMEM_BYTES <= 232448, "flame_tc: shared memory budget");
 constexpr int COEF_A = 60;
 
-// packed fp32 pairs (sm_100a FFMA2 / FMUL2): two FMAs per issue slot in the skinning epilogue
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ void tmem_ld24_nowait(uint32_t ta, uint32_t (&r)[24]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(ta));
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(ta + 8));
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]) : "r"(ta + 16));
-}
-
 struct FlameTcParams {
   int V, n_frames, m_tiles, n_tiles, total_tiles, num_kb;
   const float* base;        // [V*3] template (or the per-call static-shape template)
@@ -52,9 +37,6 @@ struct FlameTcParams {
   unsigned int* err_flag;
 };
 
-// V2 (opt-in, option "flame_v2"; not yet measured on hardware): the skinning epilogue blends the five relative transforms with
-// packed fp32 pairs (30 FFMA2 instead of 60 FFMA per vertex) and reads the accumulator one 8-vertex group ahead.
-template <bool V2>
 __global__ void __launch_bounds__(384, 1)
 flame_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FlameTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -158,49 +140,6 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 0xF1A00004u);
       tc_fence_after();
-      if constexpr (V2) {
-        f32x2 A2[COEF_A / 2];
-#pragma unroll
-        for (int i = 0; i < COEF_A / 2; ++i) A2[i] = pack2(A[2 * i], A[2 * i + 1]);
-        const uint32_t ta0 = tmem_base + lane_addr + (uint32_t)(acc * BN + half * 32 * 3);
-        uint32_t rb[2][24];
-        tmem_ld24_nowait(ta0, rb[0]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          if (g8 + 1 < 4) tmem_ld24_nowait(ta0 + (uint32_t)((g8 + 1) * 24), rb[(g8 + 1) & 1]);   // in flight during the math below
-          const int vloc0 = half * 32 + g8 * 8;
-#pragma unroll
-          for (int vv = 0; vv < 8; ++vv) {
-            const int vl = g8 * 8 + vv;
-            const float px = __uint_as_float(rb[g8 & 1][vv * 3]) + cw[160 + vl * 3], py = __uint_as_float(rb[g8 & 1][vv * 3 + 1]) + cw[160 + vl * 3 + 1],
-                        pz = __uint_as_float(rb[g8 & 1][vv * 3 + 2]) + cw[160 + vl * 3 + 2];
-            f32x2 T2[6];
-            {
-              const float w0 = cw[vl * 5];
-              const f32x2 ww = pack2(w0, w0);
-#pragma unroll
-              for (int k = 0; k < 6; ++k) T2[k] = mul2(ww, A2[k]);
-            }
-#pragma unroll
-            for (int j = 1; j < 5; ++j) {
-              const float wj = cw[vl * 5 + j];
-              const f32x2 ww = pack2(wj, wj);
-#pragma unroll
-              for (int k = 0; k < 6; ++k) T2[k] = fma2(ww, A2[j * 6 + k], T2[k]);
-            }
-            const f32x2 pxy = pack2(px, py), pz1 = pack2(pz, 1.0f);
-            float* os = out_s + row_local * OUT_PITCH + (vloc0 + vv) * 3;
-#pragma unroll
-            for (int r3 = 0; r3 < 3; ++r3) {                  // row r3 of the blended 3x4 transform: (T0 px + T2 pz) + (T1 py + T3)
-              float lo, hi;
-              unpack2(fma2(T2[2 * r3 + 1], pz1, mul2(T2[2 * r3], pxy)), lo, hi);
-              os[r3] = (lo + hi) * p.scale;
-            }
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
-      } else {
 #pragma unroll 1
       for (int g8 = 0; g8 < 4; ++g8) {                       // 8 vertices = 24 accumulator columns per iteration
         const int vloc0 = half * 32 + g8 * 8;
@@ -242,7 +181,6 @@ flame_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           os[2] = fmaf(T[8], px, fmaf(T[9], py, fmaf(T[10], pz, T[11]))) * p.scale;
         }
       }
-      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));           // accumulator free for the MMA of tile it + 2
@@ -281,10 +219,7 @@ __global__ void __launch_bounds__(256) flame_pack_kernel(const float* __restrict
   }
 }
 
-int g_flame_v2 = 0;       // option "flame_v2": packed-pair skinning epilogue with pipelined accumulator reads (opt-in until measured)
 }  // namespace
-
-void set_flame_v2(int on) { g_flame_v2 = on; }
 
 // coef: output of flame_coef_kernel; b_split: [V*3][3*KS] bf16 = [hi | hi | lo] of dirs[l_begin : l_begin + n_l]^T
 int launch_flame_tc(const FlameModel& m, const float* base, const float* coef, int coef_stride, int l_begin, int n_l,
@@ -295,8 +230,7 @@ int launch_flame_tc(const FlameModel& m, const float* base, const float* coef, i
   AT_TRY(dev_ctx(&dc));
   const int g_num_sms = dc->num_sms;
   unsigned int* const g_err_flag = dc->err_flag;
-  AT_TRY(ensure_dyn_smem((const void*)flame_tc_kernel<false>, SMEM_BYTES));
-  AT_TRY(ensure_dyn_smem((const void*)flame_tc_kernel<true>, SMEM_BYTES));
+  AT_TRY(ensure_dyn_smem((const void*)flame_tc_kernel, SMEM_BYTES));
   const int64_t total = (int64_t)n_frames * KS;
   int pgrid = (int)((total + 255) / 256);
   if (pgrid > 148 * 16) pgrid = 148 * 16;
@@ -314,8 +248,7 @@ int launch_flame_tc(const FlameModel& m, const float* base, const float* coef, i
   AT_TRY(make_map_bf16_3d(&tmB, b_split, (uint64_t)3 * KS, (uint64_t)m.V * 3, 1, (uint64_t)3 * KS * 2,
                           (uint64_t)m.V * 3 * 3 * KS * 2, BK, BN));
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  if (g_flame_v2) flame_tc_kernel<true><<<grid, 384, SMEM_BYTES, st>>>(tmA, tmB, p);
-  else flame_tc_kernel<false><<<grid, 384, SMEM_BYTES, st>>>(tmA, tmB, p);
+  flame_tc_kernel<<<grid, 384, SMEM_BYTES, st>>>(tmA, tmB, p);
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

@@ -39,6 +39,8 @@ struct TcParams {
   int tap_mode, tap_pad;   // tap mode: k-block j reads rows shifted by (j / tap_slots - tap_pad), columns of group g (piece slot j % tap_slots)
   int tap_slots;
   int exact;               // libm-accurate activations (parity-grade mode)
+  int split_slots;         // SPLIT kernels: piece slots per 64-wide K block (3 / 6); slot 0 (p0 x p0) accumulates in the main
+                           // accumulator, every other slot in the correction accumulator (see gemm_tc_kernel)
   int a_group_cols;        // column offset per group in the A view (tap mode)
   int64_t c_gs; int bias_gs;
   const float* bias; int act;
@@ -158,11 +160,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN> struct TileCfg {
+template <int BN, bool SPLIT = false> struct TileCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int ACC_COLS = SPLIT ? 2 * BN : BN;          // columns per accumulator buffer (SPLIT: main | correction)
+  static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + 8 * 4096 /*epilogue scratch, 1024-aligned: TMA store source*/;
 };
 
@@ -176,10 +179,11 @@ template <int BN> struct TileCfg {
 // Shared by the 1-CTA and the CTA-pair kernels. All 32 lanes must call it (shuffles, __syncwarp).
 constexpr int EPI_SCRATCH_BYTES = 8 * 4096;       // 8 epilogue warps x (32 rows x 128 B)
 
-template <int EPI>
+template <int EPI, int CORR_OFF = 0>
 __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, bool row_ok, int64_t c_off, int64_t g_off, int64_t r_off,
                                           const float* bias, int col0, bool gate_bf, float4* scr, int lane,
                                           const float4* rsm = nullptr, const CUtensorMap* tmo = nullptr, int row0 = 0, int bz = 0) {
+    // CORR_OFF > 0 (SPLIT kernels): the correction accumulator sits CORR_OFF columns after the main one and is added here
     // (row0, bz): first row of the warp's 32 inside its batch, batch index (output map = (cols, rows per batch, batches))
     // tmo: fp32 output tensor map (box 32 x 32, 128-byte swizzle = the scratch layout); the warp's chunk then leaves as one
     // TMA store of its scratch (rows past M are clipped by the map) instead of 8 read-back + st.global rounds per thread
@@ -215,6 +219,12 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
     }
     float v[32];
     tmem_ld32(taddr, v);
+    if constexpr (CORR_OFF > 0) {
+      float cr[32];
+      tmem_ld32(taddr + (uint32_t)CORR_OFF, cr);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += cr[j];                // one fp32 round-to-nearest add of the small terms
+    }
     if (!full && !live) return;                                  // ragged path below is per thread (no warp collectives)
     // ---- bias
     if (bias) {
@@ -368,12 +378,19 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
 }
 
 // EPI: 0 = bias/activation only, 1 = gate and/or residual operands, 2 = fused AR q/k/v epilogue
-template <int BN, int EPI>
+// SPLIT (parity-grade mode, operands are bf16 piece blocks, split.cu): the tensor core adds every MMA into its fp32 accumulator
+// with truncation, a relative loss of ~2^-24 per instruction that grows with the chain length (measured: 1e-4 relative at
+// K' = 6 x 4096). The p0 x p0 products (slot 0 of every K block) therefore get their own accumulator, whose chain is K / 16
+// instructions as in a plain bf16 GEMM, and all the correction products (2^-8 and below) a second one whose truncation
+// is negligible at that magnitude; the epilogue adds the two once. Two buffers x (main | correction) x BN columns: BN <= 128.
+template <int BN, int EPI, bool SPLIT = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmO, const TcParams p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, SPLIT>;
+  static_assert(!SPLIT || (BN <= 128 && EPI != 2), "SPLIT kernels: BN <= 128, plain or gate/residual epilogue");
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int ACC_COLS = Cfg::ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
@@ -474,15 +491,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u, p.err_flag, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        int slot = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, p.err_flag, 3);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + A_STAGE_BYTES;
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+          // SPLIT: slot 0 of a K block -> main accumulator, the others -> correction accumulator (first use of each overwrites)
+          const bool corr = SPLIT && slot != 0;
+          const uint32_t d_acc = corr ? d_tmem + (uint32_t)BN : d_tmem;
+          const int first_kb = corr ? 1 : 0;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_bf16(d_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb != first_kb || k != 0) ? 1u : 0u);
+          if (SPLIT && ++slot == p.split_slots) slot = 0;
           tc_commit(empty_bar(stage));           // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -530,7 +553,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
           for (int hd = half; hd < (bn >> 6); hd += 2) {
             float a[32], b2[32];
-            const uint32_t tcol = (uint32_t)(acc * BN + hd * 64);
+            const uint32_t tcol = (uint32_t)(acc * ACC_COLS + hd * 64);
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol, a);
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + 32, b2);
             const int col0 = col_base + hd * 64;
@@ -586,8 +609,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += 2)
-        epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, bias,
-                       col_base + c * 32, gate_bf, scr, lane, nullptr, tmo, mt * BM + q * 32, b);
+        epi_chunk<EPI, SPLIT ? BN : 0>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + c * 32), row_ok, c_off,
+                                       g_off, r_off, bias, col_base + c * 32, gate_bf, scr, lane, nullptr, tmo, mt * BM + q * 32, b);
       }
       tc_fence_before();
       __syncwarp();
@@ -925,14 +948,14 @@ int make_out_map(CUtensorMap* tmO, const GemmArgs& g, int rpb, int n_batches, bo
   return 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool SPLIT = false>
 int launch_bn_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmO, const TcParams& p,
                   cudaStream_t st) {
-  using Cfg = TileCfg<BN>;
-  AT_TRY(ensure_dyn_smem((const void*)gemm_tc_kernel<BN, EPI>, Cfg::SMEM_BYTES));
+  using Cfg = TileCfg<BN, SPLIT>;
+  AT_TRY(ensure_dyn_smem((const void*)gemm_tc_kernel<BN, EPI, SPLIT>, Cfg::SMEM_BYTES));
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   g_trace_dims[0] = p.rpb * p.n_batches; g_trace_dims[1] = p.N; g_trace_dims[2] = p.num_kb * BK * p.groups;
-  AT_CUDA(launch_k(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, tmA, tmW, tmWt, tmO, p));
+  AT_CUDA(launch_k(gemm_tc_kernel<BN, EPI, SPLIT>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, st, tmA, tmW, tmWt, tmO, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -940,6 +963,12 @@ int launch_bn_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensor
 template <int BN>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmO, const TcParams& p,
               cudaStream_t st) {
+  if constexpr (BN <= 128) {
+    if (p.split_slots) {
+      if (p.gate || p.resid) return launch_bn_epi<BN, 1, true>(tmA, tmW, tmWt, tmO, p, st);
+      return launch_bn_epi<BN, 0, true>(tmA, tmW, tmWt, tmO, p, st);
+    }
+  }
   if constexpr (BN >= 128) {
     if (p.qkv_mode) return launch_bn_epi<BN, 2>(tmA, tmW, tmWt, tmO, p, st);
   }
@@ -1019,7 +1048,7 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   AT_REQUIRE(!batched || g.M % g.a_map.rpb == 0, "gemm_tc: M must be a multiple of the A view's rows per batch");
   p.tiles_per_batch = ceil_div(p.rpb, BM);
   // CTA-pair kernel (256x256 tiles over two SMs) for the large plain GEMMs: >= 4 waves of pair tiles at >= 85 % wave efficiency
-  if (g_pair_mode && !g.tap_w && g.groups == 1 && !g.qkv_mode && g.N >= 256 && g.N % 128 == 0) {
+  if (g_pair_mode && !g.split_acc && !g.tap_w && g.groups == 1 && !g.qkv_mode && g.N >= 256 && g.N % 128 == 0) {
     const int tpb2 = ceil_div(p.rpb, 256), n_tiles_n2 = ceil_div(g.N, 256), n_cl = g_num_sms / 2;
     const long tiles2 = (long)p.n_batches * tpb2 * n_tiles_n2;
     const double row_eff = (double)p.rpb / ((double)tpb2 * 256.0);
@@ -1037,7 +1066,7 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
       p.main_tiles = (int)tiles2 - (split2 > 1 ? rem2 : 0); p.tail_split = split2; p.tail_bn = 256 / split2;
       p.total_tiles = p.main_tiles + (split2 > 1 ? rem2 * split2 : 0);
       p.num_kb = ceil_div(g.K, BK);
-      p.tap_mode = 0; p.tap_pad = 0; p.a_group_cols = 0; p.tap_slots = 1; p.exact = g.exact;
+      p.tap_mode = 0; p.tap_pad = 0; p.a_group_cols = 0; p.tap_slots = 1; p.exact = g.exact; p.split_slots = 0;
       p.c_gs = 0; p.bias_gs = 0; p.bias = g.bias; p.act = g.act;
       p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
       p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;
@@ -1092,6 +1121,7 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
     const long m_tiles = (long)g.groups * p.n_batches * p.tiles_per_batch;
     for (int i = 0; i < 4; ++i) {
       if (g.qkv_mode && cand[i] < 128) continue;                 // fused q/k/v epilogue needs whole heads per warp
+      if (g.split_acc && cand[i] > 128) continue;               // SPLIT kernels hold main + correction accumulators: BN <= 128
       if (cand[i] > 32 && cand[i] / 2 >= g.N) continue;          // tile mostly padding
       if (g_force_bn && cand[i] != g_force_bn && !(g.qkv_mode && g_force_bn < 128)) continue;
       const long tiles = m_tiles * ceil_div(g.N, cand[i]);
@@ -1119,6 +1149,9 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   p.num_kb = ceil_div(g.K, BK);
   p.tap_mode = g.tap_w > 0 ? 1 : 0; p.tap_pad = g.tap_pad; p.a_group_cols = (int)g.a_gs; p.tap_slots = g.tap_slots > 0 ? g.tap_slots : 1;
   p.exact = g.exact;
+  p.split_slots = g.split_acc;
+  AT_REQUIRE(!g.split_acc || ((g.split_acc == 3 || g.split_acc == 6) && !g.qkv_mode && (g.K / BK) % g.split_acc == 0),
+             "gemm_tc: split accumulation needs K = slots x 64 x n and a plain / gated epilogue");
   p.c_gs = g.c_gs; p.bias_gs = g.bias_gs; p.bias = g.bias; p.act = g.act;
   p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
   p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;

@@ -59,6 +59,9 @@ struct GemmArgs {
   // block of an A row holds `tap_slots` consecutive piece blocks and k-block kb reads slot kb % tap_slots of tap kb / tap_slots.
   // exact: activations use the libm-accurate functions (erff / tanhf / expf) instead of the bf16-grade fast forms
   int tap_slots; int exact;
+  // split_acc = slots (3 / 6): operands are piece blocks and the p0 x p0 products are accumulated apart from the correction
+  // products (the tensor core's accumulate truncates: see gemm_tc_kernel<.., SPLIT>); 0 = one accumulator
+  int split_acc;
 };
 static inline GemmArgs gemm_args() {
   GemmArgs g;
@@ -68,7 +71,7 @@ static inline GemmArgs gemm_args() {
   g.resid = nullptr; g.resid_map = plain_rows(0); g.out32 = nullptr; g.out_act = nullptr; g.out_act_dt = DT_F32;
   g.c_map = plain_rows(0);
   g.qkv_mode = 0; g.qkv_C = 0; g.head_scale = nullptr; g.qbuf = nullptr; g.kcache = nullptr; g.vcache = nullptr;
-  g.kv_map = plain_rows(0); g.kv_layer_stride = 0; g.skinny = 0; g.tap_slots = 1; g.exact = 0;
+  g.kv_map = plain_rows(0); g.kv_layer_stride = 0; g.skinny = 0; g.tap_slots = 1; g.exact = 0; g.split_acc = 0;
   return g;
 }
 // fp32 CUDA-core GEMM (A and W fp32). gemm_simt.cu
@@ -156,7 +159,6 @@ struct FlameModel {
   const void* bsplit_full; int ks_full;
   const void* bsplit_expr; int ks_expr;
 };
-void set_flame_v2(int on);
 int launch_flame_tc(const FlameModel& m, const float* base, const float* coef, int coef_stride, int l_begin, int n_l,
                     const void* b_split, int KS, void* a_split_ws, float* verts, int n_frames, cudaStream_t st);
 // shape (N,300) [stride 0 allowed for a shared shape row], expr (N,100), pose6 (N,6) -> verts (N,V,3)
@@ -173,6 +175,11 @@ int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int 
 // forehead EMA scan of the GAGAvatar point builder (app/GAGAvatar/models.py:120-125): points [n_frames][V][3] updated in place
 int launch_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_idx, int n_frames, float* state, int has_state,
                     float keep, cudaStream_t st);
+
+// ---------------- mesh.cu ----------------
+// area-weighted per-vertex normals (pytorch3d Meshes.verts_normals semantics) from a host-built CSR vertex adjacency
+int launch_vertex_normals(const float* verts, int64_t frame_stride, int V, const int* adj_off, const int* adj_pair, float* normals,
+                          int n_frames, cudaStream_t st);
 
 // ---------------- frontend.cu ----------------
 // torchaudio-style polyphase sinc resampling + channel mean (inference.py:112-113,230-231): in [channels][length] (channel

@@ -12,6 +12,23 @@ import torch
 from . import _lib
 
 
+def vertex_adjacency(faces: torch.Tensor, n_verts: int):
+    """CSR vertex -> incident faces for ``artalk_vertex_normals``: offsets (V+1,) int32 and pairs (E,2) int32 holding, for
+    every incidence of vertex v in a face (i0,i1,i2), the (next, prev) vertices in the face's cyclic order, so that
+    cross(P_next - P_v, P_prev - P_v) is the expression pytorch3d accumulates at that corner. Incidences of a vertex are kept
+    in face order."""
+    f = faces.detach().to("cpu", torch.int64)
+    v = torch.cat([f[:, 0], f[:, 1], f[:, 2]])
+    nxt = torch.cat([f[:, 1], f[:, 2], f[:, 0]])
+    prv = torch.cat([f[:, 2], f[:, 0], f[:, 1]])
+    order = torch.sort(v * (3 * f.shape[0]) + torch.arange(v.numel()) % f.shape[0] * 3 + torch.arange(v.numel()) // f.shape[0]).indices
+    counts = torch.bincount(v, minlength=n_verts)
+    offsets = torch.zeros(n_verts + 1, dtype=torch.int32)
+    offsets[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    pairs = torch.stack([nxt[order], prv[order]], dim=1).to(torch.int32).contiguous()
+    return offsets, pairs
+
+
 class FLAMEModel:
     N_JOINTS = 5
     MAX_FRAMES = 65536
@@ -80,6 +97,7 @@ class FLAMEModel:
         self._c = m
         self.n_verts = V
         self._ws = None
+        self._adj = None
 
     # nn.Module look-alikes used by callers of the reference class
     def to(self, device):
@@ -95,6 +113,20 @@ class FLAMEModel:
 
     def __call__(self, *a, **k):
         return self.forward(*a, **k)
+
+    def vertex_normals(self, verts: torch.Tensor, out=None) -> torch.Tensor:
+        """(N,V,3) decoded vertices -> (N,V,3) unit vertex normals over ``get_faces()`` (area-weighted, pytorch3d
+        ``Meshes.verts_normals`` semantics): what a mesh rasteriser fed with the path's output needs."""
+        if verts.dim() != 3 or verts.shape[1] != self.n_verts or verts.shape[2] != 3:
+            raise ValueError("verts must be (N, %d, 3)" % self.n_verts)
+        v = verts.to(self.device, torch.float32).contiguous()
+        if self._adj is None:
+            off, pairs = vertex_adjacency(self.faces_tensor, self.n_verts)
+            self._adj = (off.to(self.device), pairs.to(self.device))
+        normals = torch.empty_like(v) if out is None else out
+        _lib.call(self.device, _lib.lib().artalk_vertex_normals, v.data_ptr(), v.stride(0), self.n_verts, self._adj[0].data_ptr(),
+                  self._adj[1].data_ptr(), normals.data_ptr(), v.shape[0], _lib.stream_ptr(self.device))
+        return normals
 
     def forward(self, shape_params=None, expression_params=None, pose_params=None, eye_pose_params=None, verts_sclae=None, out=None):
         """shape (N,n_shape), expression (N,n_exp), pose (N,6) [global rot, jaw] or (N,3) [jaw] -> (N,V,3)*scale."""

@@ -13,10 +13,20 @@ from . import _lib
 from .flame import FLAMEModel
 
 
+#: the reference's forehead vertex list (app/GAGAvatar/models.py:326-331): FLAME topology indices, part of the wire format
+#: of the tracked-avatar pipeline (the EMA is applied to exactly these 68 vertices)
+FOREHEAD_INDICES = (
+    2168, 2165, 3068, 2199, 2196, 3720, 2091, 2088, 3524, 625, 628, 3871, 705, 708, 2030, 667, 670,
+    3708, 3706, 3729, 3721, 3773, 3789, 3735, 3732, 3786, 3876, 3878, 3913, 3899, 3872, 3874, 3864, 3865,
+    3158, 3157, 336, 335, 3153, 3705, 2177, 2176, 3540, 671, 672, 3863, 2134, 16, 17, 2138, 2139,
+    2567, 2566, 337, 338, 3154, 3712, 2178, 2179, 3495, 674, 673, 3868, 2135, 27, 18, 1429, 1430,
+)
+
+
 class GagaPointBuilder:
-    def __init__(self, flame_model: FLAMEModel, shapecode: torch.Tensor, forehead_indices, keep: float = 0.98):
+    def __init__(self, flame_model: FLAMEModel, shapecode: torch.Tensor, forehead_indices=FOREHEAD_INDICES, keep: float = 0.98):
         """``flame_model`` built with ``scale=5.0`` (models.py:20), ``shapecode`` (1,300) of the tracked avatar,
-        ``forehead_indices`` the reference's vertex list (models.py:326)."""
+        ``forehead_indices`` the reference's vertex list (models.py:326-331, the default)."""
         if shapecode.dim() != 2 or shapecode.shape[0] != 1:
             raise ValueError("shapecode must be (1, n_shape)")
         self.flame = flame_model

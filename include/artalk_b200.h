@@ -159,6 +159,15 @@ int artalk_resample_mono(const float* in, int channels, int64_t ch_stride, int64
 int artalk_ema_scan(float* points, int64_t frame_stride, const int* idx, int n_idx, int n_frames, float* state, int has_state,
                     float keep, void* stream);
 
+/* Vertex normals for a mesh rasteriser fed with the decoded vertices (the reference builds pytorch3d Meshes(verts, faces),
+ * app/flame_model/renderer_utils.py; FLAMEModel.get_faces, app/flame_model/FLAME.py:68-69): area-weighted sum of the incident
+ * faces' normals cross(P_next - P_v, P_prev - P_v), normalised with eps 1e-6 (pytorch3d verts_normals semantics). The
+ * vertex -> incident-face adjacency is CSR: adj_offsets [n_verts + 1], adj_pairs [2 * adj_offsets[n_verts]] = the (next, prev)
+ * vertex of every incidence in the face's cyclic order (artalk_b200/flame.py::vertex_adjacency builds it from the faces).
+ * verts / normals [n_frames][n_verts][3] fp32 (frame_stride of verts in floats). */
+int artalk_vertex_normals(const float* verts, int64_t frame_stride, int n_verts, const int* adj_offsets, const int* adj_pairs,
+                          float* normals, int n_frames, void* stream);
+
 /* --- measurement hooks (bench.py) ---
  * artalk_launch_count: kernels launched by this library in this process so far.
  * artalk_profile_enable(e, 1): bracket every GEMM / attention launch of the engine with CUDA events on the launching
@@ -196,6 +205,7 @@ typedef struct artalk_gemm {
   float* out32; void* out_act; int out_act_dt; artalk_rowmap_t c_map;
   int tap_slots;                 /* bf16 kernel, tap mode on piece blocks: slots per 64-column block (0 / 1 = plain operands) */
   int exact;                     /* bf16 kernel: 1 = libm-accurate activations (parity-grade mode) */
+  int split_acc;                 /* bf16 kernel on piece blocks: slots (3 / 6) -> the p0 x p0 products get their own accumulator */
 } artalk_gemm_t;
 /* out = resid + gate * act(A W^T + bias); precision selects the fp32 CUDA-core or the bf16 tcgen05 kernel */
 int artalk_op_gemm(const artalk_gemm_t* g, int precision, void* stream);

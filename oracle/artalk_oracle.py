@@ -366,8 +366,9 @@ def get_flame_verts(asset, shape_params, motion, with_global=False, scale=1.0):
 
 def gaga_t_points(asset, shapecode, motion, forehead_indices, scale=5.0, keep=0.98):
     """app/GAGAvatar/models.py:112-126 run frame by frame like the reference's render loop (inference.py:78-84):
-    FLAME(scale 5.0, avatar shape, pose [0,0,0,jaw], zero eye pose) then the forehead EMA. Parity unpinned: importing the
-    reference's GAGAvatar module needs torchvision / pytorch3d / the tracked-avatar assets, none of which exist here."""
+    FLAME(scale 5.0, avatar shape, pose [0,0,0,jaw], zero eye pose) then the forehead EMA. Pinned against the live
+    ``GAGAvatar.build_forward_batch`` (rasteriser / pytorch3d imports stubbed, called frame by frame on a stand-in ``self``
+    holding a synthetic tracked avatar) by oracle/make_golden.py::run_gaga -> tests/golden/gaga.npz."""
     idx = torch.as_tensor(list(forehead_indices), dtype=torch.long)
     out, upper = [], None
     for f in range(motion.shape[0]):
@@ -381,3 +382,17 @@ def gaga_t_points(asset, shapecode, motion, forehead_indices, scale=5.0, keep=0.
             pts[:, idx] = upper
         out.append(pts[0])
     return torch.stack(out, 0)
+
+
+def vertex_normals(verts: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """pytorch3d ``Meshes.verts_normals`` (what the reference's mesh renderer shades with, app/flame_model/renderer_utils.py
+    builds Meshes(verts, faces); pytorch3d is not installed here, so this restates its published formula: PARITY UNPINNED):
+    at every corner of every face accumulate the cross product of the two edges leaving that corner, normalise with eps 1e-6.
+    verts (N,V,3), faces (F,3) -> (N,V,3)."""
+    f = faces.long()
+    v0, v1, v2 = verts[:, f[:, 0]], verts[:, f[:, 1]], verts[:, f[:, 2]]
+    n = torch.zeros_like(verts)
+    n.index_add_(1, f[:, 1], torch.cross(v2 - v1, v0 - v1, dim=-1))
+    n.index_add_(1, f[:, 2], torch.cross(v0 - v2, v1 - v2, dim=-1))
+    n.index_add_(1, f[:, 0], torch.cross(v1 - v0, v2 - v0, dim=-1))
+    return torch.nn.functional.normalize(n, eps=1e-6, dim=-1)

@@ -76,3 +76,14 @@ def flame_inputs():
     motion = 0.3 * torch.randn(n, 106, generator=g)
     motion[0, 100:] = 0.0           # exact zero rotation exercises the ||r+1e-8|| quirk
     return shape, motion
+
+
+GAGA_CASE = dict(seed=11, n_frames=12)
+
+
+def gaga_inputs():
+    """Motion codes of consecutive frames + the tracked avatar's shape code for the GAGAvatar point builder (f4)."""
+    g = torch.Generator().manual_seed(GAGA_CASE["seed"])
+    motion = 0.3 * torch.randn(GAGA_CASE["n_frames"], 106, generator=g)
+    shape = 0.5 * torch.randn(1, 300, generator=g)
+    return motion, shape

@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 from artalk_b200 import synthetic                      # noqa: E402
 from oracle import reference_live as live              # noqa: E402
 from oracle.artalk_oracle import Oracle, get_flame_verts  # noqa: E402
-from oracle.cases import CASES, flame_inputs          # noqa: E402
+from oracle.cases import CASES, flame_inputs, gaga_inputs          # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 COND_STRIDE = 32
@@ -204,6 +204,41 @@ def run_flame(report):
     print("flame", dev)
 
 
+def run_gaga(report):
+    """``GAGAvatar.build_forward_batch`` (app/GAGAvatar/models.py:98-128) called frame by frame like the render loop
+    (inference.py:78-84) on a stand-in ``self`` holding a synthetic tracked avatar: FLAME(scale 5) + forehead EMA. The
+    rasteriser extension and pytorch3d are stubbed (never executed on this leg); ``transform_emoca_to_p3d`` (camera matrix from
+    the global rotation, pytorch3d) is replaced because it does not touch ``t_points``."""
+    import types
+    from types import SimpleNamespace
+    live._stub_modules()
+    if live.REF_ROOT not in sys.path:
+        sys.path.insert(0, live.REF_ROOT)
+
+    class _Any:
+        def __init__(self, *a, **k): pass
+        def __call__(self, *a, **k): return _Any()
+        def __getattr__(self, n): return _Any()
+    m = types.ModuleType("diff_gaussian_rasterization_32d")
+    m.GaussianRasterizationSettings = _Any
+    m.GaussianRasterizer = _Any
+    sys.modules.setdefault("diff_gaussian_rasterization_32d", m)
+    import app.GAGAvatar.models as gm
+    asset = synthetic.make_flame_asset(0)
+    fm = live.load_flame(asset, scale=5.0)
+    gm.transform_emoca_to_p3d = lambda r: torch.eye(4)[None, :3].repeat(r.shape[0], 1, 1)
+    motion, shape = gaga_inputs()
+    me = SimpleNamespace(_tracked_id={"image": torch.zeros(3, 64, 64), "transform_matrix": torch.eye(4)[:3], "shapecode": shape[0]})
+    pts = torch.stack([gm.GAGAvatar.build_forward_batch(me, motion[i:i + 1].clone(), fm)["t_points"][0] for i in range(motion.shape[0])])
+    from oracle.artalk_oracle import gaga_t_points
+    o = gaga_t_points(asset, shape, motion, gm.forehead_indices)
+    idx = torch.as_tensor(gm.forehead_indices)
+    np.savez_compressed(os.path.join(GOLD, "gaga.npz"), forehead=pts[:, idx].numpy(), strided=pts[:, ::8].numpy(),
+                        forehead_indices=np.asarray(gm.forehead_indices, dtype=np.int32))
+    report["gaga"] = {"t_points_maxabs": float((o - pts).abs().max()), "n_frames": int(motion.shape[0])}
+    print("gaga", report["gaga"])
+
+
 def main():
     if not live.available():
         raise SystemExit("reference not found at %s" % live.REF_ROOT)
@@ -223,6 +258,8 @@ def main():
         run_engine_case(report, "full_eng1", 750)
     if not only or "flame" in only:
         run_flame(report)
+    if not only or "gaga" in only:
+        run_gaga(report)
     path = os.path.join(GOLD, "PIN_REPORT.json")
     old = {}
     if only and os.path.exists(path):

@@ -21,9 +21,9 @@ def rowmap(rpb=0, bs=0, rs=0):
 
 def run_gemm(precision, A, W, M, N, K, *, a_map=None, bias=None, act=0, gate=None, gate_map=None, resid=None,
              resid_map=None, out32=None, out_act=None, c_map=None, tap_w=0, tap_pad=0, groups=1, a_gs=0, w_gs=0, c_gs=0,
-             bias_gs=0, ldw=None, tap_slots=0, exact=0):
+             bias_gs=0, ldw=None, tap_slots=0, exact=0, split_acc=0):
     g = _lib.Gemm()
-    g.tap_slots, g.exact = tap_slots, exact
+    g.tap_slots, g.exact, g.split_acc = tap_slots, exact, split_acc
     g.A, g.W = A.data_ptr(), W.data_ptr()
     g.a_map = a_map or rowmap(0, 0, K)
     g.ldw = ldw if ldw is not None else K
@@ -312,7 +312,7 @@ def test_split_gemm_is_fp32_grade(slots, tol, M, N, K, act):
     b = torch.randn(N, generator=g).to(dev())
     As, Ws = split_op(A, slots, 0), split_op(W, slots, 1)
     out = torch.full((M, N), float("nan"), device=dev())
-    run_gemm(1, As, Ws, M, N, slots * K, bias=b, act=act, out32=out, exact=1)
+    run_gemm(1, As, Ws, M, N, slots * K, bias=b, act=act, out32=out, exact=1, split_acc=slots)
     pre = A.double() @ W.double().t() + b.double()
     ref = ACTS[act](pre)
     mag = (A.double().abs() @ W.double().abs().t()).clamp_min(1.0)           # error scale of a length-K dot product
@@ -336,7 +336,7 @@ def test_split_conv_window_and_tap_views(slots, tol):
     out = torch.empty(n * L_out, Cc, device=dev())
     S = slots
     run_gemm(1, split_op(x, S, 0), split_op(wp, S, 1), n * L_out, Cc, S * k * Cc, a_map=rowmap(L_out, S * L_in * Cc, S * s * Cc),
-             bias=b, out32=out, exact=1)
+             bias=b, out32=out, exact=1, split_acc=S)
     ref = F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), stride=s).transpose(1, 2).reshape(n * L_out, Cc)
     assert ((out.double() - ref).abs().max().item()) < tol * 40
     # positional conv: grouped, k=128, pad 64, GELU + residual
@@ -349,7 +349,7 @@ def test_split_conv_window_and_tap_views(slots, tol):
     out = torch.empty(n * Fr, H, device=dev())
     run_gemm(1, split_op(h, S, 0), split_op(wp, S, 1), n * Fr, gw, S * K * gw, a_map=rowmap(Fr, S * Fr * H, S * H), tap_w=gw,
              tap_pad=K // 2, groups=G, a_gs=gw, w_gs=S * gw * K * gw, c_gs=gw, bias_gs=gw, bias=b, act=1, resid=h.view(-1, H),
-             resid_map=rowmap(0, 0, H), out32=out, c_map=rowmap(0, 0, H), ldw=S * K * gw, tap_slots=S, exact=1)
+             resid_map=rowmap(0, 0, H), out32=out, c_map=rowmap(0, 0, H), ldw=S * K * gw, tap_slots=S, exact=1, split_acc=S)
     pc = F.conv1d(h.double().transpose(1, 2), w.double(), b.double(), padding=K // 2, groups=G)[:, :, :-1]
     ref = h.double() + F.gelu(pc).transpose(1, 2)
     assert (out.double() - ref.reshape(n * Fr, H)).abs().max().item() < tol * 40

@@ -24,6 +24,7 @@ DEV = "cuda:0"
 torch.set_num_threads(os.cpu_count() or 1)
 
 MOTION_TOL = {"fp32": 1e-3, "bf16": 2e-2, "bf16x3": 1e-3, "bf16x6": 1e-3}
+BF16_LOGIT_MAX, BF16_LOGIT_MEAN, BF16_BIT_MARGIN, BF16_FLIP_RATE = 0.2, 0.03, 0.15, 0.008
 
 _models = {}
 
@@ -194,8 +195,8 @@ def check_contract(m, case, g, precision, name):
     return rec
 
 
-@pytest.mark.parametrize("precision", PARITY_MODES)
 @pytest.mark.parametrize("name", ["tiny_style", "tiny_null", "tiny_ragged", "full_10s", "full_eng1", "full_30s"])
+@pytest.mark.parametrize("precision", PARITY_MODES)            # outer loop (one weight set resident at a time)
 def test_inference_meets_bit_exact_contract(name, precision):
     """fp32 and the parity-grade tensor-core modes against the live reference's stored outputs: TINY cases, the 10 s clip,
     BASELINE configs[0]'s demo/eng1.wav (4 chunks, ragged tail) and a 30 s / 8-chunk clip (clip_length 750, configs[2]/[3])."""
@@ -248,16 +249,24 @@ def test_inference_bf16_teacher_forced(name):
     out = m.inference({"audio": case.audio(), "style_motion": case.style()}, trace=tr, teacher_words=gold_words,
                       teacher_prev_words=gold_prev)
     err = np.abs(tr["logits"].cpu().numpy() - g["logits"])
-    assert err.max() < 0.6 and err.mean() < 0.04, (err.max(), err.mean())
-    safe = gu.margins(g["logits"]) > 0.6
+    mg = gu.margins(g["logits"])
     bits = unpack_words(tr["words"]).cpu()
     gb = gu.unpack_bits(g["bits"])
-    assert int(((bits != gb) & safe).sum()) == 0
-    assert (bits != gb).float().mean().item() < 0.06
+    flips = bits != gb
+    prev_frac = (unpack_words(tr["prev_words"]).cpu() != gu.unpack_bits(g["prev_bits"])).float().mean().item()
+    merr = np.abs(out.cpu().numpy() - g["motion"]).max()
+    _record("bf16_teacher_forced", dict(case=name, logit_max=float(err.max()), logit_mean=float(err.mean()), flips=int(flips.sum()),
+                                        flip_rate=float(flips.float().mean()), max_margin_of_flip=float(mg[flips].max()) if flips.any() else 0.0,
+                                        motion_max=float(merr), prev_flip_frac=prev_frac))
+    # measured on B200 (round 2, full_10s): logits max 0.097 / mean 0.0147, 66 of 17 376 bits flipped (0.38 %), largest reference
+    # margin among the flipped bits 0.077, motion max 0.017. Thresholds = those values with ~2x headroom
+    assert err.max() < BF16_LOGIT_MAX and err.mean() < BF16_LOGIT_MEAN, (err.max(), err.mean())
+    assert int((flips & (mg > BF16_BIT_MARGIN)).sum()) == 0
+    assert flips.float().mean().item() < BF16_FLIP_RATE
     # given the same bits in, every chunk's decode is within the bf16 tolerance of the reference
-    assert np.abs(out.cpu().numpy() - g["motion"]).max() < MOTION_TOL["bf16"]
+    assert merr < MOTION_TOL["bf16"]
     # re-encoded bits: sign decisions on a bf16-noisy encoder output
-    assert (unpack_words(tr["prev_words"]).cpu() != gu.unpack_bits(g["prev_bits"])).float().mean().item() < 0.08
+    assert prev_frac < 0.08
 
 
 @pytest.mark.parametrize("name", ["tiny_style", "full_10s"])
@@ -295,7 +304,7 @@ def test_latency_mode_within_bf16_tolerance():
             m.set_latency_mode(False)
         res[on] = (tr["logits"].float().cpu(), out.cpu(), free.cpu())
     err = np.abs(res[True][0].numpy() - g["logits"])
-    assert err.max() < 0.6 and err.mean() < 0.04, (err.max(), err.mean())
+    assert err.max() < BF16_LOGIT_MAX and err.mean() < BF16_LOGIT_MEAN, (err.max(), err.mean())
     assert np.abs(res[True][1].numpy() - g["motion"]).max() < MOTION_TOL["bf16"]
     d = (res[True][0] - res[False][0]).abs()
     assert d.max().item() < 0.3 and d.mean().item() < 0.02, (d.max().item(), d.mean().item())
