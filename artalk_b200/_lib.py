@@ -61,7 +61,7 @@ class Attn(C.Structure):
         ("dt", C.c_int), ("n_seq", C.c_int), ("n_heads", C.c_int), ("head_dim", C.c_int), ("lq", C.c_int), ("lk", C.c_int),
         ("q_ss", C.c_int64), ("q_rs", C.c_int64), ("k_ss", C.c_int64), ("k_rs", C.c_int64),
         ("v_ss", C.c_int64), ("v_rs", C.c_int64), ("o_ss", C.c_int64), ("o_rs", C.c_int64),
-        ("scale", C.c_float), ("split", C.c_int),
+        ("scale", C.c_float), ("split", C.c_int), ("key_bound", C.c_void_p),
     ]
 
 
@@ -150,6 +150,10 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"attn_simt_max_lq", int(os.environ["ARTALK_ATTN_SIMT_MAX_LQ"]))
         if os.environ.get("ARTALK_SKINNY_MAX_M"):         # 0: the latency-path kernels (skinny.cu) are never taken
             l.artalk_set_option(b"skinny_max_m", int(os.environ["ARTALK_SKINNY_MAX_M"]))
+        if os.environ.get("ARTALK_ATTN_BOUND"):            # 0: AR attention keeps the max pass (A/B switch)
+            l.artalk_set_option(b"attn_bound", int(os.environ["ARTALK_ATTN_BOUND"]))
+        if os.environ.get("ARTALK_ATTN_POLY"):
+            l.artalk_set_option(b"attn_poly", int(os.environ["ARTALK_ATTN_POLY"]))
         if os.environ.get("ARTALK_SKINNY_TOKENS"):
             l.artalk_set_option(b"skinny_tokens", int(os.environ["ARTALK_SKINNY_TOKENS"]))
         if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":

@@ -191,6 +191,9 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "gemm_tma_resid")) { set_gemm_tma_resid(value); return AT_OK; }
   if (!std::strcmp(name, "attn_simt_max_lq")) { set_attn_simt_max_lq(value); return AT_OK; }
   if (!std::strcmp(name, "skinny_tokens")) { g_skinny_tokens = value; return AT_OK; }
+  if (!std::strcmp(name, "attn_bound")) { g_attn_bound = value; return AT_OK; }
+  if (!std::strcmp(name, "attn_poly")) { set_attn_poly(value); return AT_OK; }
+  if (!std::strcmp(name, "w2v_graph_chunks")) { g_w2v_graph_chunks = value; return AT_OK; }
   if (!std::strcmp(name, "skinny_max_m")) { set_skinny_max_m(value); return AT_OK; }
   set_last_error("artalk_set_option: unknown option '%s'", name);
   return AT_EINVAL;
@@ -230,6 +233,7 @@ int artalk_op_attention(const artalk_attn_t* a, void* stream) {
   x.q = a->q; x.k = a->k; x.v = a->v; x.out = a->out; x.dt = a->dt; x.n_seq = a->n_seq; x.n_heads = a->n_heads;
   x.head_dim = a->head_dim; x.lq = a->lq; x.lk = a->lk; x.q_ss = a->q_ss; x.q_rs = a->q_rs; x.k_ss = a->k_ss; x.k_rs = a->k_rs;
   x.v_ss = a->v_ss; x.v_rs = a->v_rs; x.o_ss = a->o_ss; x.o_rs = a->o_rs; x.scale = a->scale; x.split = a->split;
+  x.key_bound = a->key_bound;
   return launch_attention(x, (cudaStream_t)stream);
 }
 

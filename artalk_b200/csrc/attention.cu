@@ -9,17 +9,28 @@ namespace artalk {
 
 namespace {
 constexpr int KT = 64;        // keys per shared-memory tile
-constexpr int RPW = 4;        // query rows per warp (register blocking)
-constexpr int WARPS = 4;
 
-template <typename T, int D>
+// RPW query rows per warp (register blocking: every K / V element read from shared memory feeds RPW FMAs), WARPS warps per
+// block. <4, 4> (16 rows per block, 41 KB static-size footprint) serves the few-row AR steps; <8, 8> (64 rows per block) the
+// long sequences of the fp32 data-flow modes (wav2vec 199 rows, VAE 100 / 200, AR 50 / 100): twice the FMAs per shared-memory
+// load and a quarter of the K / V tile loads.
+template <int D, int RPW, int WARPS> struct AttnSmem {
+  static constexpr int KS = KT * (D + 1), VS = KT * D, QS = WARPS * D * RPW, PS = WARPS * KT * RPW;
+  static constexpr int BYTES = (KS + VS + QS + PS) * 4;
+};
+
+template <typename T, int D, int RPW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) attn_kernel(AttnArgs a) {
   pdl_enter();
+  static_assert(RPW % 4 == 0, "rows per warp are read as float4 groups");
   constexpr int DPL = D / 32;                 // output dims per lane
-  __shared__ float Ks[KT][D + 1];
-  __shared__ __align__(16) float Vs[KT][D];
-  __shared__ __align__(16) float Qs[WARPS][D][RPW];
-  __shared__ __align__(16) float Ps[WARPS][KT][RPW];
+  constexpr int R4 = RPW / 4;
+  using SM = AttnSmem<D, RPW, WARPS>;
+  extern __shared__ __align__(16) float attn_smem[];
+  float (*Vs)[D] = reinterpret_cast<float (*)[D]>(attn_smem);                                   // [KT][D]
+  float (*Qs)[D][RPW] = reinterpret_cast<float (*)[D][RPW]>(attn_smem + SM::VS);                // [WARPS][D][RPW]
+  float (*Ps)[KT][RPW] = reinterpret_cast<float (*)[KT][RPW]>(attn_smem + SM::VS + SM::QS);     // [WARPS][KT][RPW]
+  float (*Ks)[D + 1] = reinterpret_cast<float (*)[D + 1]>(attn_smem + SM::VS + SM::QS + SM::PS); // [KT][D + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int head = blockIdx.y, seq = blockIdx.z;
   const int q0 = blockIdx.x * (WARPS * RPW) + warp * RPW;
@@ -68,12 +79,15 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(AttnArgs a) {
     for (int r = 0; r < RPW; ++r) s[r][0] = s[r][1] = 0.f;
 #pragma unroll 8
     for (int d = 0; d < D; ++d) {
-      float4 q4 = *reinterpret_cast<const float4*>(&Qs[warp][d][0]);
-      float ka = Ks[lane][d], kc = Ks[lane + 32][d];
-      s[0][0] = fmaf(q4.x, ka, s[0][0]); s[0][1] = fmaf(q4.x, kc, s[0][1]);
-      s[1][0] = fmaf(q4.y, ka, s[1][0]); s[1][1] = fmaf(q4.y, kc, s[1][1]);
-      s[2][0] = fmaf(q4.z, ka, s[2][0]); s[2][1] = fmaf(q4.z, kc, s[2][1]);
-      s[3][0] = fmaf(q4.w, ka, s[3][0]); s[3][1] = fmaf(q4.w, kc, s[3][1]);
+      const float ka = Ks[lane][d], kc = Ks[lane + 32][d];
+#pragma unroll
+      for (int g = 0; g < R4; ++g) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&Qs[warp][d][4 * g]);
+        s[4 * g][0] = fmaf(q4.x, ka, s[4 * g][0]); s[4 * g][1] = fmaf(q4.x, kc, s[4 * g][1]);
+        s[4 * g + 1][0] = fmaf(q4.y, ka, s[4 * g + 1][0]); s[4 * g + 1][1] = fmaf(q4.y, kc, s[4 * g + 1][1]);
+        s[4 * g + 2][0] = fmaf(q4.z, ka, s[4 * g + 2][0]); s[4 * g + 2][1] = fmaf(q4.z, kc, s[4 * g + 2][1]);
+        s[4 * g + 3][0] = fmaf(q4.w, ka, s[4 * g + 3][0]); s[4 * g + 3][1] = fmaf(q4.w, kc, s[4 * g + 3][1]);
+      }
     }
     float p[RPW][2];
 #pragma unroll
@@ -91,19 +105,27 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(AttnArgs a) {
       for (int j = 0; j < DPL; ++j) acc[r][j] *= corr;
       p[r][0] = p0; p[r][1] = p1;
     }
-    *reinterpret_cast<float4*>(&Ps[warp][lane][0]) = make_float4(p[0][0], p[1][0], p[2][0], p[3][0]);
-    *reinterpret_cast<float4*>(&Ps[warp][lane + 32][0]) = make_float4(p[0][1], p[1][1], p[2][1], p[3][1]);
+#pragma unroll
+    for (int g = 0; g < R4; ++g) {
+      *reinterpret_cast<float4*>(&Ps[warp][lane][4 * g]) = make_float4(p[4 * g][0], p[4 * g + 1][0], p[4 * g + 2][0], p[4 * g + 3][0]);
+      *reinterpret_cast<float4*>(&Ps[warp][lane + 32][4 * g]) = make_float4(p[4 * g][1], p[4 * g + 1][1], p[4 * g + 2][1], p[4 * g + 3][1]);
+    }
     __syncwarp();
     int kmax = min(KT, lk_blk - k0);
     for (int key = 0; key < kmax; ++key) {
-      float4 p4 = *reinterpret_cast<const float4*>(&Ps[warp][key][0]);
+      float vv[DPL];
 #pragma unroll
-      for (int j = 0; j < DPL; ++j) {
-        float vv = Vs[key][lane + 32 * j];
-        acc[0][j] = fmaf(p4.x, vv, acc[0][j]);
-        acc[1][j] = fmaf(p4.y, vv, acc[1][j]);
-        acc[2][j] = fmaf(p4.z, vv, acc[2][j]);
-        acc[3][j] = fmaf(p4.w, vv, acc[3][j]);
+      for (int j = 0; j < DPL; ++j) vv[j] = Vs[key][lane + 32 * j];
+#pragma unroll
+      for (int g = 0; g < R4; ++g) {
+        const float4 p4 = *reinterpret_cast<const float4*>(&Ps[warp][key][4 * g]);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+          acc[4 * g][j] = fmaf(p4.x, vv[j], acc[4 * g][j]);
+          acc[4 * g + 1][j] = fmaf(p4.y, vv[j], acc[4 * g + 1][j]);
+          acc[4 * g + 2][j] = fmaf(p4.z, vv[j], acc[4 * g + 2][j]);
+          acc[4 * g + 3][j] = fmaf(p4.w, vv[j], acc[4 * g + 3][j]);
+        }
       }
     }
     __syncwarp();
@@ -118,6 +140,19 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(AttnArgs a) {
     for (int j = 0; j < DPL; ++j) ob[(int64_t)qi * a.o_rs + lane + 32 * j] = from_f32<T>(acc[r][j] * inv);
   }
 }
+
+template <typename T, int D, int RPW, int WARPS>
+int launch_simt(const AttnArgs& a, cudaStream_t st) {
+  constexpr int smem = AttnSmem<D, RPW, WARPS>::BYTES;
+  AT_TRY(ensure_dyn_smem((const void*)attn_kernel<T, D, RPW, WARPS>, smem));
+  dim3 grid(ceil_div(a.lq, WARPS * RPW), a.n_heads, a.n_seq);
+  AT_CUDA(launch_k(attn_kernel<T, D, RPW, WARPS>, grid, dim3(WARPS * 32), (size_t)smem, st, a));
+  return AT_OK;
+}
+template <typename T, int D>
+int launch_simt_rows(const AttnArgs& a, cudaStream_t st) {
+  return a.lq > 32 ? launch_simt<T, D, 8, 8>(a, st) : launch_simt<T, D, 4, 4>(a, st);
+}
 }  // namespace
 
 int g_attn_simt_max_lq = 0;     // bf16 launches with at most this many query rows take the SIMT kernel (option "attn_simt_max_lq")
@@ -130,13 +165,12 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   AT_REQUIRE(a.lk > 0 && a.k_rs % 4 == 0 && a.v_rs % 4 == 0 && a.k_ss % 4 == 0 && a.v_ss % 4 == 0,
              "attention: key/value strides must be multiples of 4");
   g_trace_dims[0] = a.n_seq * a.n_heads; g_trace_dims[1] = a.lq; g_trace_dims[2] = a.lk;
-  dim3 grid(ceil_div(a.lq, WARPS * RPW), a.n_heads, a.n_seq);
   if (a.dt == DT_F32) {
-    if (a.head_dim == 64) AT_CUDA(launch_k(attn_kernel<float, 64>, dim3(grid), dim3(WARPS * 32), 0, st, a));
-    else AT_CUDA(launch_k(attn_kernel<float, 32>, dim3(grid), dim3(WARPS * 32), 0, st, a));
+    if (a.head_dim == 64) AT_TRY((launch_simt_rows<float, 64>(a, st)));
+    else AT_TRY((launch_simt_rows<float, 32>(a, st)));
   } else {
-    if (a.head_dim == 64) AT_CUDA(launch_k(attn_kernel<bf16, 64>, dim3(grid), dim3(WARPS * 32), 0, st, a));
-    else AT_CUDA(launch_k(attn_kernel<bf16, 32>, dim3(grid), dim3(WARPS * 32), 0, st, a));
+    if (a.head_dim == 64) AT_TRY((launch_simt_rows<bf16, 64>(a, st)));
+    else AT_TRY((launch_simt_rows<bf16, 32>(a, st)));
   }
   AT_LAUNCH_CHECK();
   return AT_OK;

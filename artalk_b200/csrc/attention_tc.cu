@@ -44,6 +44,7 @@ struct AttnTcParams {
   int h0;                    // keys held in buffer 0 (= lk_pad when ping-pong)
   int n_stages, stage_bytes, kv_bytes;
   float scale_log2e;
+  const float* bound;        // per-head bound of the scaled scores (null: row maxima from a first pass over S)
   bf16* out; int64_t o_ss, o_rs;
   unsigned int* err_flag;
 };
@@ -71,6 +72,19 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA / integer pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5] (magic-number rounding), 2^f by a
+// degree-3 polynomial (max relative error 7.7e-5, far below the bf16 rounding of P, 3.9e-3), n added to the exponent field.
+// The softmax loop is bound by the 16 ex2 per clock of the MUFU unit (26 600 per 128 x 208 tile); sending a fraction of the
+// elements through this path balances the two pipes (option "attn_poly").
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                     // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.05508868396282196f, f, 0.24260404706001282f);
+  p = fmaf(p, f, 0.6932762265205383f);
+  p = fmaf(p, f, 0.9999289512634277f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 // MN-major operand tile (V: rows = keys (K dim), 64 contiguous head dims = one 128 B swizzle row):
 // canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> 8-key groups 1024 B apart (SBO); a single 64-wide N block
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
@@ -85,6 +99,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// POLY: 0 = every exponential on the MUFU unit, 1 = one in four on the FMA pipe (ex2_poly), 2 = one in two
+template <int POLY>
 __global__ void __launch_bounds__(384, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
@@ -231,8 +247,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_after();
       // ---- pass 1: row maximum. 16 columns per step; the next step's tcgen05.ld is in flight while this one is reduced
       // (4 independent running maxima: a single fmax chain would cost 4 cycles per column)
+      // (skipped when the caller bounds the scores: one pass over S instead of two)
+      const bool bounded = p.bound != nullptr;
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      {
+      if (!bounded) {
         uint32_t sa[16], sb[16];
         auto reduce = [&](const uint32_t (&s)[16], int c) {
           const int base = c * 16;
@@ -256,14 +274,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
       }
-      float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      if (SK) {
+      float m = bounded ? __ldg(p.bound + h) : fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      if (SK && !bounded) {
         volatile float* xm = xch + ((0 * 2 + (it & 1)) * 2) * 128;
         xm[wg * 128 + row] = m;
         named_bar_sync(1, 256);
         m = fmaxf(xm[row], xm[128 + row]);
       }
-      const float ms = (m == -INFINITY) ? 0.f : m * p.scale_log2e;
+      const float ms = (m == -INFINITY) ? 0.f : m * (bounded ? 1.4426950408889634f : p.scale_log2e);
       // ---- pass 2: P = exp2(S * scale - max) as bf16 pairs over the S columns already consumed; row sum.
       // Double-buffered 16-column loads; two independent partial sums
       float sum2[2] = {0.f, 0.f};
@@ -276,8 +294,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (base + 16 <= lk_r) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              const float p0 = ex2(fmaf(__uint_as_float(s0[j]), p.scale_log2e, -ms));
-              const float p1 = ex2(fmaf(__uint_as_float(s0[j + 1]), p.scale_log2e, -ms));
+              const float x0 = fmaf(__uint_as_float(s0[j]), p.scale_log2e, -ms), x1 = fmaf(__uint_as_float(s0[j + 1]), p.scale_log2e, -ms);
+              const float p0 = ex2(x0);
+              const float p1 = (POLY == 2 || (POLY == 1 && (j & 2))) ? ex2_poly(x1) : ex2(x1);      // compile-time choice per element
               sum2[(j >> 1) & 1] += p0 + p1;
               __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
               pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
@@ -370,6 +389,9 @@ int make_map(CUtensorMap* m, const void* base, uint64_t width, uint64_t rows, ui
 
 }  // namespace
 
+int g_attn_poly = 0;       // option "attn_poly": share of the softmax exponentials computed on the FMA pipe (0, 1 = 1/4, 2 = 1/2)
+void set_attn_poly(int v) { g_attn_poly = v < 0 ? 0 : (v > 2 ? 2 : v); }
+
 bool attention_tc_supported(const AttnArgs& a) {
   return a.dt == DT_BF16 && a.head_dim == 64 && a.lk <= MAX_LK && a.lk >= 1 && a.q_rs % 8 == 0 && a.k_rs % 8 == 0 &&
          a.v_rs % 8 == 0 && a.q_ss % 8 == 0 && a.k_ss % 8 == 0 && a.v_ss % 8 == 0 && a.o_rs % 8 == 0 && a.o_ss % 8 == 0 &&
@@ -383,7 +405,9 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   AT_TRY(dev_ctx(&dc));
   const int g_num_sms = dc->num_sms;
   unsigned int* const g_err_flag = dc->err_flag;
-  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel, SMEM_LIMIT));
+  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<0>, SMEM_LIMIT));
+  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<1>, SMEM_LIMIT));
+  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<2>, SMEM_LIMIT));
   AttnTcParams p;
   p.n_heads = a.n_heads; p.lq = a.lq; p.lk = a.lk;
   p.lk_pad = (a.lk + 15) & ~15;
@@ -399,6 +423,7 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   AT_REQUIRE(p.n_stages >= 1, "attention_tc: %d keys do not fit in shared memory", a.lk);
   p.split = a.split;
   p.scale_log2e = a.scale * 1.4426950408889634f;
+  p.bound = a.key_bound;
   p.out = (bf16*)a.out; p.o_ss = a.o_ss; p.o_rs = a.o_rs;
   p.err_flag = g_err_flag;
   CUtensorMap tmQ, tmK, tmV, tmK2, tmV2;
@@ -416,7 +441,9 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)p.n_stages * p.stage_bytes + fixed;
   const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
   g_trace_dims[0] = a.n_seq * a.n_heads; g_trace_dims[1] = a.lq; g_trace_dims[2] = a.lk;
-  AT_CUDA(launch_k(attn_tc_kernel, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
+  if (g_attn_poly == 2) AT_CUDA(launch_k(attn_tc_kernel<2>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
+  else if (g_attn_poly == 1) AT_CUDA(launch_k(attn_tc_kernel<1>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
+  else AT_CUDA(launch_k(attn_tc_kernel<0>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

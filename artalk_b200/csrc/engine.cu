@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <array>
 #include <mutex>
 #include <set>
@@ -152,6 +153,15 @@ int Engine::finalize() {
   for (int i = 0; i < c.n_levels; ++i) { tb.pn[i] = c.patch_nums[i]; cum += c.patch_nums[i]; tb.cum[i] = cum; }
   tb.up_i0 = get<int>("tb.up_i0"); tb.up_i1 = get<int>("tb.up_i1"); tb.up_w1 = get<float>("tb.up_w1");
   tb.pool_start = get<int>("tb.pool_start"); tb.pool_end = get<int>("tb.pool_end");
+  // |q.k| <= head_scale[h] in the AR attention (both L2-normalised). With bound <= 32 the smallest exponent, 2^(-2*32*log2 e)
+  // = 2^-92, is a normal fp32 / bf16 number, so the bound can replace the row maximum
+  ar_bound_ok = true;
+  for (int l = 0; l < c.ar_depth; ++l) {
+    float hs[64];
+    AT_REQUIRE(c.ar_heads <= 64, "ar_heads");
+    AT_CUDA(cudaMemcpy(hs, get<float>(S("ar.l%d.head_scale", l)), sizeof(float) * c.ar_heads, cudaMemcpyDeviceToHost));
+    for (int h = 0; h < c.ar_heads; ++h) ar_bound_ok = ar_bound_ok && hs[h] > 0.f && hs[h] <= 32.0f;
+  }
   // parity-grade mode: bf16 piece blocks of every tensor-core weight, once per weight set
   free_split();
   if (split_slots()) {
@@ -299,6 +309,8 @@ bool g_pdl = true;
 int g_skinny_tokens = 1;        // AR scale steps with at most this many new tokens per clip take the latency kernels (option "skinny_tokens")
 int g_pdl_mask = 3;            // measured in the chunk graph: GEMM/attention edges help (-3.4 %), elementwise edges cancel it
 int g_pdl_w2v_max_chunks = 1 << 30;
+int g_w2v_graph_chunks = 4;     // option "w2v_graph_chunks": wav2vec calls with at most this many chunks replay a CUDA graph
+int g_attn_bound = 1;          // option "attn_bound": AR attention subtracts the per-head score bound instead of the row maximum
 
 // ------------------------------------------------------------------ launch trace
 bool g_trace_on = false;
@@ -420,6 +432,19 @@ int Engine::audio_encode(const float* audio, int n_chunks, float* cond, cudaStre
   AT_REQUIRE(finalized, "engine not finalized");
   if (n_chunks <= 0) return AT_OK;
   size_t per = audio_ws_per_chunk();
+  if (n_chunks <= g_w2v_graph_chunks) {
+    // streaming / few-chunk calls are launch bound on the host (~190 launches of 5-8 us kernels per chunk): the encoder body
+    // runs from a CUDA graph like the AR chunk, with the audio staged in and the conditioning staged out of the workspace
+    const size_t in_b = (size_t)n_chunks * cfg.chunk_samples * 4, out_b = (size_t)n_chunks * L * cfg.w2v_hidden * 4;
+    AT_TRY(ws_reserve((size_t)n_chunks * per + in_b + out_b + (2 << 20), st));
+    WS(a_in, float*, in_b);
+    WS(c_out, float*, out_b);
+    const size_t body_mark = ws_off;
+    AT_CUDA(cudaMemcpyAsync(a_in, audio, in_b, cudaMemcpyDeviceToDevice, st));
+    AT_TRY(run_graphed(0x40000000 | n_chunks, st, body_mark, [&](cudaStream_t s) { return audio_encode_sub(a_in, n_chunks, c_out, s); }));
+    AT_CUDA(cudaMemcpyAsync(cond, c_out, out_b, cudaMemcpyDeviceToDevice, st));
+    return AT_OK;
+  }
   int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_chunks, ws_limit / per));
   AT_TRY(ws_reserve((size_t)sub * per + (1 << 20), st));
   for (int c0 = 0; c0 < n_chunks; c0 += sub) {
@@ -688,6 +713,89 @@ int Engine::vae_encode_bits(const float* motion, int n, uint32_t* words_out, flo
   return AT_OK;
 }
 
+// ------------------------------------------------------------------ CUDA-graph replay of a fixed-address body
+// `body` only touches fixed workspace addresses (everything it allocates comes from the workspace after `body_mark`, a
+// deterministic function of `key`), so after one eager warm-up per key it is captured and replayed. The caller's stream may be
+// the legacy default stream, which cannot be captured: capture and replay run on an internal stream fenced against the
+// caller's stream with events. A graph is stale when the workspace was re-allocated (addresses) or a process-wide option
+// changed which kernels a launch selects. A failed capture / instantiation switches the engine to eager launches and says so.
+int Engine::run_graphed(int key, cudaStream_t st, size_t body_mark, const std::function<int(cudaStream_t)>& body) {
+  if (use_graphs && !prof && !g_trace_on) {
+    auto it = graphs.find(key);
+    if (it != graphs.end() && (it->second.ws_base != ws || it->second.epoch != g_option_epoch.load())) {
+      if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+      graphs.erase(it);
+      it = graphs.end();
+    }
+    if (it == graphs.end()) {
+      GraphEntry ge; ge.exec = nullptr; ge.ws_base = ws; ge.warm = 0; ge.n_launches = 0; ge.epoch = g_option_epoch.load();
+      it = graphs.insert(std::make_pair(key, ge)).first;
+    }
+    GraphEntry& ge = it->second;
+    if (!gstream) {
+      AT_CUDA(cudaStreamCreateWithFlags(&gstream, cudaStreamNonBlocking));
+      AT_CUDA(cudaEventCreateWithFlags(&gev_in, cudaEventDisableTiming));
+      AT_CUDA(cudaEventCreateWithFlags(&gev_out, cudaEventDisableTiming));
+    }
+    if (!ge.exec && ge.warm >= 1) {
+      // second call for this key: capture the body
+      cudaGraph_t graph = nullptr;
+      AT_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));
+      const int rc = body(gstream);
+      const cudaError_t ce = cudaStreamEndCapture(gstream, &graph);
+      ws_off = body_mark;
+      if (rc != AT_OK || ce != cudaSuccess || !graph) {
+        const cudaError_t sticky = cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        use_graphs = false;                                          // eager launches from here on, and say so
+        graph_failure = S("capture of graph %d failed (body status %d, cudaStreamEndCapture: %s / %s)", key, rc,
+                          cudaGetErrorString(ce), cudaGetErrorString(sticky));
+        fprintf(stderr, "[artalk_b200] WARNING: %s; this engine now launches eagerly (slower)\n", graph_failure.c_str());
+        if (rc != AT_OK) return rc;
+      } else {
+        if (getenv("ARTALK_DEBUG")) {
+          size_t ne = 0;
+          if (cudaGraphGetEdges_v2(graph, nullptr, nullptr, nullptr, &ne) == cudaSuccess && ne > 0) {
+            std::vector<cudaGraphNode_t> from(ne), to(ne);
+            std::vector<cudaGraphEdgeData> ed(ne);
+            size_t prog = 0;
+            if (cudaGraphGetEdges_v2(graph, from.data(), to.data(), ed.data(), &ne) == cudaSuccess)
+              for (size_t i = 0; i < ne; ++i) prog += ed[i].type == cudaGraphDependencyTypeProgrammatic;
+            fprintf(stderr, "[artalk] captured graph %d: %zu edges, %zu programmatic (PDL)\n", key, ne, prog);
+          }
+          cudaGetLastError();
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+          cudaGetLastError();
+          ge.exec = nullptr; use_graphs = false;
+          graph_failure = S("cudaGraphInstantiate of graph %d failed: %s", key, cudaGetErrorString(ie));
+          fprintf(stderr, "[artalk_b200] WARNING: %s; this engine now launches eagerly (slower)\n", graph_failure.c_str());
+        }
+      }
+    }
+    if (ge.exec) {
+      AT_CUDA(cudaEventRecord(gev_in, st));
+      AT_CUDA(cudaStreamWaitEvent(gstream, gev_in, 0));
+      AT_CUDA(cudaGraphLaunch(ge.exec, gstream));
+      ++graph_replays;
+      AT_CUDA(cudaEventRecord(gev_out, gstream));
+      AT_CUDA(cudaStreamWaitEvent(st, gev_out, 0));
+      g_launch_count.fetch_add(ge.n_launches, std::memory_order_relaxed);
+      return AT_OK;
+    }
+    if (use_graphs) {
+      const unsigned long long l0 = g_launch_count.load();
+      AT_TRY(body(st));
+      ge.n_launches = g_launch_count.load() - l0;
+      ge.warm++;
+      return AT_OK;
+    }
+  }
+  return body(st);
+}
+
 // ------------------------------------------------------------------ one 100-frame chunk of the AR recurrence
 // The chunk body only reads/writes fixed workspace addresses, so after one eager warm-up per (clips, teacher forcing)
 // it is captured into a CUDA graph and replayed: ~700 launches per chunk become one graph launch (launch gaps dominate
@@ -723,87 +831,9 @@ int Engine::ar_chunk(int B, const float* cond, int64_t cond_cs, const float* sty
   AT_CUDA(cudaMemcpyAsync(prev_ws, prev_words, (size_t)BL * 4, cudaMemcpyDeviceToDevice, st));
   if (forced_words) AT_CUDA(cudaMemcpyAsync(forced_ws, forced_words, (size_t)BL * 4, cudaMemcpyDeviceToDevice, st));
 
-  const bool can_graph = use_graphs && !prof && !g_trace_on;
-  const int key = B * 2 + (forced_words ? 1 : 0);
-  bool launched = false;
-  if (can_graph) {
-    auto it = graphs.find(key);
-    // stale: the workspace was re-allocated (addresses), or a process-wide option changed which kernels a launch selects
-    if (it != graphs.end() && (it->second.ws_base != ws || it->second.epoch != g_option_epoch.load())) {
-      if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
-      graphs.erase(it);
-      it = graphs.end();
-    }
-    if (it == graphs.end()) {
-      GraphEntry ge; ge.exec = nullptr; ge.ws_base = ws; ge.warm = 0; ge.n_launches = 0; ge.epoch = g_option_epoch.load();
-      it = graphs.insert(std::make_pair(key, ge)).first;
-    }
-    GraphEntry& ge = it->second;
-    // the caller's stream may be the legacy default stream, which cannot be captured: capture and replay on an
-    // internal stream that is fenced against the caller's stream with events
-    if (!gstream) {
-      AT_CUDA(cudaStreamCreateWithFlags(&gstream, cudaStreamNonBlocking));
-      AT_CUDA(cudaEventCreateWithFlags(&gev_in, cudaEventDisableTiming));
-      AT_CUDA(cudaEventCreateWithFlags(&gev_out, cudaEventDisableTiming));
-    }
-    if (!ge.exec && ge.warm >= 1) {
-      // second call for this key: capture the body
-      cudaGraph_t graph = nullptr;
-      AT_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeThreadLocal));
-      int rc = ar_chunk_body(B, scond, style_ws, prev_ws, motion_ws, words_ws, logits_ws, forced_words ? forced_ws : nullptr, enc_ws,
-                             gstream);
-      cudaError_t ce = cudaStreamEndCapture(gstream, &graph);
-      ws_off = body_mark;
-      if (rc != AT_OK || ce != cudaSuccess || !graph) {
-        const cudaError_t sticky = cudaGetLastError();
-        if (graph) cudaGraphDestroy(graph);
-        use_graphs = false;                                          // eager launches from here on, and say so
-        graph_failure = S("capture of the chunk graph failed (body status %d, cudaStreamEndCapture: %s / %s)", rc,
-                          cudaGetErrorString(ce), cudaGetErrorString(sticky));
-        fprintf(stderr, "[artalk_b200] WARNING: %s; this engine now launches the chunk body eagerly (slower)\n", graph_failure.c_str());
-        if (rc != AT_OK) return rc;
-      } else {
-        if (getenv("ARTALK_DEBUG")) {
-          size_t ne = 0;
-          if (cudaGraphGetEdges_v2(graph, nullptr, nullptr, nullptr, &ne) == cudaSuccess && ne > 0) {
-            std::vector<cudaGraphNode_t> from(ne), to(ne);
-            std::vector<cudaGraphEdgeData> ed(ne);
-            size_t prog = 0;
-            if (cudaGraphGetEdges_v2(graph, from.data(), to.data(), ed.data(), &ne) == cudaSuccess)
-              for (size_t i = 0; i < ne; ++i) prog += ed[i].type == cudaGraphDependencyTypeProgrammatic;
-            fprintf(stderr, "[artalk] captured chunk graph: %zu edges, %zu programmatic (PDL)\n", ne, prog);
-          }
-          cudaGetLastError();
-        }
-        cudaError_t ie = cudaGraphInstantiate(&ge.exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ie != cudaSuccess) {
-          cudaGetLastError();
-          ge.exec = nullptr; use_graphs = false;
-          graph_failure = S("cudaGraphInstantiate of the chunk graph failed: %s", cudaGetErrorString(ie));
-          fprintf(stderr, "[artalk_b200] WARNING: %s; this engine now launches the chunk body eagerly (slower)\n", graph_failure.c_str());
-        }
-      }
-    }
-    if (ge.exec) {
-      AT_CUDA(cudaEventRecord(gev_in, st));
-      AT_CUDA(cudaStreamWaitEvent(gstream, gev_in, 0));
-      AT_CUDA(cudaGraphLaunch(ge.exec, gstream));
-      ++graph_replays;
-      AT_CUDA(cudaEventRecord(gev_out, gstream));
-      AT_CUDA(cudaStreamWaitEvent(st, gev_out, 0));
-      g_launch_count.fetch_add(ge.n_launches, std::memory_order_relaxed);
-      launched = true;
-    } else if (use_graphs) {
-      unsigned long long l0 = g_launch_count.load();
-      AT_TRY(ar_chunk_body(B, scond, style_ws, prev_ws, motion_ws, words_ws, logits_ws, forced_words ? forced_ws : nullptr, enc_ws, st));
-      ge.n_launches = g_launch_count.load() - l0;
-      ge.warm++;
-      launched = true;
-    }
-  }
-  if (!launched)
-    AT_TRY(ar_chunk_body(B, scond, style_ws, prev_ws, motion_ws, words_ws, logits_ws, forced_words ? forced_ws : nullptr, enc_ws, st));
+  AT_TRY(run_graphed(B * 2 + (forced_words ? 1 : 0), st, body_mark, [&](cudaStream_t s) {
+    return ar_chunk_body(B, scond, style_ws, prev_ws, motion_ws, words_ws, logits_ws, forced_words ? forced_ws : nullptr, enc_ws, s);
+  }));
   AT_CUDA(cudaMemcpyAsync(motion_out, motion_ws, (size_t)B * Tm * c.motion_dim * 4, cudaMemcpyDeviceToDevice, st));
   AT_CUDA(cudaMemcpyAsync(prev_words, prev_ws, (size_t)BL * 4, cudaMemcpyDeviceToDevice, st));
   if (words_out) AT_CUDA(cudaMemcpyAsync(words_out, words_ws, (size_t)BL * 4, cudaMemcpyDeviceToDevice, st));
@@ -893,6 +923,7 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
       a.lq = n_new; a.lk = P + off + n_new;          // prev chunk + every current token of scale <= p
       a.q_ss = (int64_t)n_new * C; a.q_rs = C; a.k_ss = a.v_ss = (int64_t)KV * C; a.k_rs = a.v_rs = C;
       a.o_ss = (int64_t)n_new * C; a.o_rs = C; a.scale = 1.0f; a.split = 0;
+      if (ar_bound_ok && g_attn_bound) a.key_bound = get<float>(S("ar.l%d.head_scale", l));
       AT_TRY(attention(a, st));
       g = gemm_args();
       g.A = o; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.proj.w", l)); g.ldw = C; g.M = M; g.N = C; g.K = C;

@@ -106,11 +106,16 @@ struct AttnArgs {
   int64_t o_ss, o_rs;
   float scale;
   int split;                          // >0: query rows < split only see keys < split (bitwise_vae.py:67-76)
+  // optional [n_heads] device array: an upper bound of |q.k| * scale for every row of head h (the AR attention's q and k are
+  // L2-normalised per head, app/transformer.py:72-74, so |q.k| <= head_scale[h]). The tcgen05 kernel then subtracts the bound
+  // instead of the row maximum (softmax is shift invariant) and skips its max pass over S; ignored by the SIMT kernel
+  const float* key_bound = nullptr;
 };
 // dispatch: bf16 / head_dim 64 / <= 384 keys -> tcgen05 kernel (attention_tc.cu), otherwise the fp32-arithmetic SIMT kernel
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 bool attention_tc_supported(const AttnArgs& a);
 void set_attn_simt_max_lq(int v);
+void set_attn_poly(int v);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 // AR q/k/v post-processing (app/transformer.py:71-74): per-head L2 normalise q (x exp(min(scale_mul, ln100))) and k,
 // q -> qbuf [M, C]; k,v -> cache rows given by kv_map. qkv: [M, 3C] (q | k | v), or [M, 2C] (k | v) when has_q = 0.

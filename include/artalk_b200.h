@@ -220,6 +220,7 @@ typedef struct artalk_attn {
   int64_t q_ss, q_rs, k_ss, k_rs, v_ss, v_rs, o_ss, o_rs;
   float scale;
   int split;
+  const float* key_bound;        /* optional [n_heads] device array: |q.k| * scale <= key_bound[h] (bf16 tensor-core kernel: one pass) */
 } artalk_attn_t;
 int artalk_op_attention(const artalk_attn_t* a, void* stream);
 int artalk_op_layernorm(const float* x, void* out, int out_dt, const float* gamma, const float* beta, int rows, int cols,

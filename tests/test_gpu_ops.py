@@ -15,6 +15,9 @@ def dev():
     return torch.device("cuda:0")
 
 
+ATTN_POLY_DEFAULT = 0          # library default of option "attn_poly" (tests that toggle it restore this)
+
+
 def rowmap(rpb=0, bs=0, rs=0):
     return _lib.RowMap(rpb, bs, rs)
 
@@ -355,8 +358,9 @@ def test_split_conv_window_and_tap_views(slots, tol):
     assert (out.double() - ref.reshape(n * Fr, H)).abs().max().item() < tol * 40
 
 
-def run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, scale, split=0):
+def run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, scale, split=0, key_bound=None):
     a = _lib.Attn()
+    a.key_bound = _lib.ptr(key_bound)
     a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     a.dt = _lib.F32 if q.dtype == torch.float32 else _lib.BF16
     a.n_seq, a.n_heads, a.head_dim, a.lq, a.lk = n_seq, H, D, lq, lk
@@ -381,6 +385,51 @@ def test_attention(dt, tol, n_seq, H, D, lq, lk, split):
     out.fill_(float("nan"))
     run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), scale, split)
     _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol)
+
+
+@pytest.mark.parametrize("poly", [1, 2])
+@pytest.mark.parametrize("n_seq,H,lq,lk,split", [(3, 16, 199, 199, 0), (2, 8, 200, 200, 100), (2, 12, 100, 362, 0)])
+def test_attention_polynomial_exp2(poly, n_seq, H, lq, lk, split):
+    """Option attn_poly: one in four / one in two softmax exponentials run on the FMA pipe (degree-3 exp2, 7.7e-5 relative)
+    instead of the MUFU unit; same tolerance against the fp32 reference as the MUFU-only kernel."""
+    D = 64
+    g = torch.Generator(device="cpu").manual_seed(lq + 7 * lk)
+    Cw = H * D
+    q = torch.randn(n_seq, lq, Cw, generator=g).to(dev(), torch.bfloat16)
+    k = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), torch.bfloat16)
+    v = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), torch.bfloat16)
+    out = torch.full((n_seq, lq, Cw), float("nan"), device=dev(), dtype=torch.bfloat16)
+    _lib.check(_lib.lib().artalk_set_option(b"attn_poly", poly))
+    try:
+        run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), 0.3, split)
+    finally:
+        _lib.check(_lib.lib().artalk_set_option(b"attn_poly", ATTN_POLY_DEFAULT))
+    _check_attn(out, q, k, v, n_seq, H, D, lq, lk, 0.3, split, 2e-2)
+
+
+@pytest.mark.parametrize("n_seq,H,lq,lk", [(4, 12, 25, 212), (5, 12, 1, 182), (2, 12, 100, 362), (3, 12, 50, 262), (7, 12, 5, 187)])
+def test_attention_bounded_scores_single_pass(n_seq, H, lq, lk):
+    """AR attention (app/transformer.py:72-77): q and k are L2-normalised per head and q is scaled by the head's
+    exp(min(scale_mul, ln 100)), so |q.k| <= head_scale[h]. Given that bound the tcgen05 kernel skips its row-maximum pass
+    (softmax is shift invariant): same result as the two-pass kernel and the fp32 reference, over ping-pong (<= 256 keys) and
+    split-key (> 256 keys) items, from 1 to 100 query rows, with scales from 1 to 30."""
+    D = 64
+    g = torch.Generator(device="cpu").manual_seed(lq * 5 + lk)
+    Cw = H * D
+    hs = torch.linspace(1.0, 30.0, H)
+    q = F.normalize(torch.randn(n_seq, lq, H, D, generator=g), dim=-1) * hs.view(1, 1, H, 1)
+    k = F.normalize(torch.randn(n_seq, lk, H, D, generator=g), dim=-1)
+    q = q.reshape(n_seq, lq, Cw).to(dev(), torch.bfloat16)
+    k = k.reshape(n_seq, lk, Cw).to(dev(), torch.bfloat16)
+    v = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), torch.bfloat16)
+    strides = (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw)
+    outs = []
+    for bound in (hs.to(dev()), None):
+        out = torch.full((n_seq, lq, Cw), float("nan"), device=dev(), dtype=torch.bfloat16)
+        run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, 1.0, 0, key_bound=bound)
+        _check_attn(out, q, k, v, n_seq, H, D, lq, lk, 1.0, 0, 2e-2)
+        outs.append(out.float())
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-2
 
 
 def _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol):
