@@ -248,7 +248,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---- pass 1: row maximum. 16 columns per step; the next step's tcgen05.ld is in flight while this one is reduced
       // (4 independent running maxima: a single fmax chain would cost 4 cycles per column)
       // (skipped when the caller bounds the scores: one pass over S instead of two)
-      const bool bounded = p.bound != nullptr;
+      // A head takes the bound only if exp2(-2 * bound * log2 e) stays a normal number (bound <= 32): warp- and item-uniform
+      const float bnd = p.bound ? __ldg(p.bound + h) : 0.f;
+      const bool bounded = bnd > 0.f && bnd <= 32.0f;
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       if (!bounded) {
         uint32_t sa[16], sb[16];
@@ -274,7 +276,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
       }
-      float m = bounded ? __ldg(p.bound + h) : fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      float m = bounded ? bnd : fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       if (SK && !bounded) {
         volatile float* xm = xch + ((0 * 2 + (it & 1)) * 2) * 128;
         xm[wg * 128 + row] = m;

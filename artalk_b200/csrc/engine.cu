@@ -153,15 +153,6 @@ int Engine::finalize() {
   for (int i = 0; i < c.n_levels; ++i) { tb.pn[i] = c.patch_nums[i]; cum += c.patch_nums[i]; tb.cum[i] = cum; }
   tb.up_i0 = get<int>("tb.up_i0"); tb.up_i1 = get<int>("tb.up_i1"); tb.up_w1 = get<float>("tb.up_w1");
   tb.pool_start = get<int>("tb.pool_start"); tb.pool_end = get<int>("tb.pool_end");
-  // |q.k| <= head_scale[h] in the AR attention (both L2-normalised). With bound <= 32 the smallest exponent, 2^(-2*32*log2 e)
-  // = 2^-92, is a normal fp32 / bf16 number, so the bound can replace the row maximum
-  ar_bound_ok = true;
-  for (int l = 0; l < c.ar_depth; ++l) {
-    float hs[64];
-    AT_REQUIRE(c.ar_heads <= 64, "ar_heads");
-    AT_CUDA(cudaMemcpy(hs, get<float>(S("ar.l%d.head_scale", l)), sizeof(float) * c.ar_heads, cudaMemcpyDeviceToHost));
-    for (int h = 0; h < c.ar_heads; ++h) ar_bound_ok = ar_bound_ok && hs[h] > 0.f && hs[h] <= 32.0f;
-  }
   // parity-grade mode: bf16 piece blocks of every tensor-core weight, once per weight set
   free_split();
   if (split_slots()) {
@@ -923,7 +914,9 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
       a.lq = n_new; a.lk = P + off + n_new;          // prev chunk + every current token of scale <= p
       a.q_ss = (int64_t)n_new * C; a.q_rs = C; a.k_ss = a.v_ss = (int64_t)KV * C; a.k_rs = a.v_rs = C;
       a.o_ss = (int64_t)n_new * C; a.o_rs = C; a.scale = 1.0f; a.split = 0;
-      if (ar_bound_ok && g_attn_bound) a.key_bound = get<float>(S("ar.l%d.head_scale", l));
+      // |q.k| <= head_scale[h] (q and k are L2-normalised per head): the tcgen05 kernel subtracts that bound instead of the row
+      // maximum for every head whose scale is small enough (<= 32) and skips its max pass over S
+      if (g_attn_bound) a.key_bound = get<float>(S("ar.l%d.head_scale", l));
       AT_TRY(attention(a, st));
       g = gemm_args();
       g.A = o; g.a_map = plain_rows(C); g.W = getw(S("ar.l%d.proj.w", l)); g.ldw = C; g.M = M; g.N = C; g.K = C;

@@ -87,9 +87,6 @@ struct Engine {
   int run_graphed(int key, cudaStream_t st, size_t body_mark, const std::function<int(cudaStream_t)>& body);
   bool use_graphs = true;
   cudaStream_t gstream = nullptr; cudaEvent_t gev_in = nullptr, gev_out = nullptr;
-  // every AR head scale exp(min(scale_mul, ln 100)) is small enough that exp(s - bound) cannot underflow: the AR attention
-  // passes the per-head scale as the softmax bound (one pass over S)
-  bool ar_bound_ok = false;
   int latency_rows = 0;      // artalk_set_latency_mode: GEMMs with at most this many rows take the latency kernel (0 = off)
   void drop_graphs() {
     for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);

@@ -66,7 +66,9 @@ int launch_savgol_post(const float* motion, float* out, int n_clips, int T, int 
 // app/GAGAvatar/models.py:120-125, run frame by frame by the reference: the first frame ever initialises the state with its
 // own points, every later frame does u <- 0.98 u + 0.02 c and the frame's forehead vertices are REPLACED by u. Batched here
 // as a scan over the frames of one call: one thread per (forehead vertex, coordinate), sequential over frames (a first-order
-// IIR, <= 750 steps), state carried across calls in `state` [n_idx][3].
+// IIR), state carried across calls in `state` [n_idx][3]. The recurrence is sequential but the loads are not: every thread requests
+// the values of the next 32 frames (60 KB apart: one HBM / L2 line each) before it walks them, so a call costs one memory
+// round trip per 32 frames instead of one per frame (16 000 frames: 8.7 ms -> measured in profiles/).
 __global__ void __launch_bounds__(128) ema_scan_kernel(float* __restrict__ points, int64_t frame_stride, const int* __restrict__ idx,
                                                        int n_idx, int n_frames, float* __restrict__ state, int has_state, float keep) {
   pdl_enter();
@@ -75,10 +77,18 @@ __global__ void __launch_bounds__(128) ema_scan_kernel(float* __restrict__ point
   const int v = idx[t / 3], c = t % 3;
   float* p = points + (int64_t)v * 3 + c;
   float u = has_state ? state[t] : 0.f;
-  for (int f = 0; f < n_frames; ++f, p += frame_stride) {
-    const float cur = *p;
-    if (f == 0 && !has_state) u = cur;                       // models.py:120-121: no blending on the very first frame
-    else { u = keep * u + (1.0f - keep) * cur; *p = u; }     // models.py:123-125
+  constexpr int PF = 32;
+  for (int f0 = 0; f0 < n_frames; f0 += PF) {
+    float cur[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) cur[i] = (f0 + i < n_frames) ? p[(int64_t)i * frame_stride] : 0.f;       // independent loads
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      if (f0 + i >= n_frames) break;
+      if (f0 + i == 0 && !has_state) u = cur[i];             // models.py:120-121: no blending on the very first frame
+      else { u = keep * u + (1.0f - keep) * cur[i]; p[(int64_t)i * frame_stride] = u; }     // models.py:123-125
+    }
+    p += (int64_t)PF * frame_stride;
   }
   state[t] = u;
 }

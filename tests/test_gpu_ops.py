@@ -412,11 +412,12 @@ def test_attention_bounded_scores_single_pass(n_seq, H, lq, lk):
     """AR attention (app/transformer.py:72-77): q and k are L2-normalised per head and q is scaled by the head's
     exp(min(scale_mul, ln 100)), so |q.k| <= head_scale[h]. Given that bound the tcgen05 kernel skips its row-maximum pass
     (softmax is shift invariant): same result as the two-pass kernel and the fp32 reference, over ping-pong (<= 256 keys) and
-    split-key (> 256 keys) items, from 1 to 100 query rows, with scales from 1 to 30."""
+    split-key (> 256 keys) items, from 1 to 100 query rows, with scales from 1 to 30; a head at the clamp (100 > 32) keeps its max pass."""
     D = 64
     g = torch.Generator(device="cpu").manual_seed(lq * 5 + lk)
     Cw = H * D
     hs = torch.linspace(1.0, 30.0, H)
+    hs[H - 1] = 100.0                                      # the clamp value (ln 100): this head keeps the max pass
     q = F.normalize(torch.randn(n_seq, lq, H, D, generator=g), dim=-1) * hs.view(1, 1, H, 1)
     k = F.normalize(torch.randn(n_seq, lk, H, D, generator=g), dim=-1)
     q = q.reshape(n_seq, lq, Cw).to(dev(), torch.bfloat16)
@@ -429,7 +430,7 @@ def test_attention_bounded_scores_single_pass(n_seq, H, lq, lk):
         run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, 1.0, 0, key_bound=bound)
         _check_attn(out, q, k, v, n_seq, H, D, lq, lk, 1.0, 0, 2e-2)
         outs.append(out.float())
-    assert (outs[0] - outs[1]).abs().max().item() < 1e-2
+    assert (outs[0] - outs[1]).abs().max().item() < 4e-2        # the two evaluations differ by bf16 ulps of P and of the output (|v| <= 4)
 
 
 def _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol):

@@ -370,6 +370,26 @@ def test_strict_state_dict():
         m.audio_cond(torch.zeros(1, 64000))                       # nothing loaded -> loud failure
 
 
+def test_engine_on_a_non_current_device():
+    """`device="cuda:1"` while the process's current device is 0. Every C-ABI call runs under the engine's device and
+    the library keeps SM counts / error flags / shared-memory opt-ins per device ordinal, so both devices work in one process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = CASES["tiny_style"]
+    a, s = case.audio(), case.style()
+    assert torch.cuda.current_device() == 0
+    ref = model("TINY", "bf16").inference({"audio": a, "style_motion": s}).cpu()
+    m1 = BitwiseARModel(config.TINY, device="cuda:1", precision="bf16")
+    m1.load_state_dict(gu.state_dict("TINY"))
+    out = m1.inference({"audio": a, "style_motion": s})
+    assert out.device == torch.device("cuda:1") and torch.cuda.current_device() == 0
+    assert torch.equal(out.cpu(), ref)
+    fm = FLAMEModel(n_shape=300, n_exp=100, scale=1.0, no_lmks=True, asset=synthetic.make_flame_asset(0), device="cuda:1")
+    v = m1.basic_vae.get_flame_verts(fm, torch.zeros(1, 300, device="cuda:1").expand(out.shape[1], -1), out[0], with_global=True)
+    assert v.device == torch.device("cuda:1") and bool(torch.isfinite(v).all())
+    m1.close()
+
+
 # ----------------------------------------------------------------------------- FLAME + engine surface
 @pytest.mark.parametrize("fprec", ["tc", "fp32"])
 def test_flame_matches_golden_and_oracle(fprec):

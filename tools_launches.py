@@ -9,6 +9,7 @@ import csv, sys, re, collections, argparse
 ap = argparse.ArgumentParser()
 ap.add_argument("csv"); ap.add_argument("--which", type=int, default=-2, help="index of the step to summarise (python index into the list of steps)")
 ap.add_argument("--detail", action="store_true")
+ap.add_argument("--all", action="store_true", help="the file holds exactly one step (bench.py --profile-step --steps 1 --warmup 0): summarise all of it")
 a = ap.parse_args()
 rows = []
 for r in csv.reader(l for l in open(a.csv) if l.startswith('"')):
@@ -20,7 +21,7 @@ names = [r[ik] for r in rows]
 starts = [i for i, n in enumerate(names) if "audio_stats_kernel" in n]
 bounds = starts + [len(rows)]
 steps = [(bounds[i], bounds[i + 1]) for i in range(len(starts))]
-s0, s1 = steps[a.which]
+s0, s1 = (0, len(rows)) if a.all else steps[a.which]
 def short(n):
     n = re.sub(r"^void ", "", n)
     n = re.sub(r"\(.*$", "", n)
