@@ -192,6 +192,7 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "attn_simt_max_lq")) { set_attn_simt_max_lq(value); return AT_OK; }
   if (!std::strcmp(name, "skinny_tokens")) { g_skinny_tokens = value; return AT_OK; }
   if (!std::strcmp(name, "attn_bound")) { g_attn_bound = value; return AT_OK; }
+  if (!std::strcmp(name, "posconv4")) { g_posconv4 = value; return AT_OK; }
   if (!std::strcmp(name, "attn_poly")) { set_attn_poly(value); return AT_OK; }
   if (!std::strcmp(name, "w2v_graph_chunks")) { g_w2v_graph_chunks = value; return AT_OK; }
   if (!std::strcmp(name, "skinny_max_m")) { set_skinny_max_m(value); return AT_OK; }
@@ -235,6 +236,12 @@ int artalk_op_attention(const artalk_attn_t* a, void* stream) {
   x.v_ss = a->v_ss; x.v_rs = a->v_rs; x.o_ss = a->o_ss; x.o_rs = a->o_rs; x.scale = a->scale; x.split = a->split;
   x.key_bound = a->key_bound;
   return launch_attention(x, (cudaStream_t)stream);
+}
+
+int artalk_op_posconv4(const void* x, const void* w4, const float* bias, const float* resid, float* out, int n_chunks, int frames,
+                       int hidden, int groups, int taps, void* stream) {
+  AT_REQUIRE(x && w4 && bias && resid && out && resid != out, "null or aliased argument");
+  return launch_posconv4(x, w4, bias, resid, out, n_chunks, frames, hidden, groups, taps, (cudaStream_t)stream);
 }
 
 int artalk_op_layernorm(const float* x, void* out, int out_dt, const float* gamma, const float* beta, int rows, int cols,

@@ -183,6 +183,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 extern bool g_pdl;        // host switch (artalk_enable_pdl); default on
 extern int g_pdl_w2v_max_chunks;   // wav2vec sub-batches larger than this run without PDL (option "pdl_w2v_max_chunks")
 extern int g_skinny_tokens;   // option "skinny_tokens" (engine.cu)
+extern int g_posconv4;        // option "posconv4" (engine.cu)
 extern int g_attn_bound;      // option "attn_bound" (engine.cu)
 extern int g_w2v_graph_chunks;   // option "w2v_graph_chunks" (engine.cu)
 extern int g_pdl_mask;    // per kernel class (option "pdl_mask"): 1 = tcgen05 GEMM, 2 = tcgen05 attention, 4 = everything else

@@ -147,6 +147,13 @@ int Engine::finalize() {
       return AT_EINVAL;
     }
   }
+  if (const Tensor* w4 = find("w2v.pos.w4")) {      // optional: shifted filter copies of the positional conv (bf16 mode)
+    const int64_t want = (int64_t)c.w2v_pos_groups * 256 * (c.w2v_pos_kernel + 3) * 64;
+    if (w4->dt != DT_BF16 || w4->numel != want) {
+      set_last_error("finalize: tensor 'w2v.pos.w4' has dtype %d numel %lld, expected bf16 numel %lld", w4->dt, (long long)w4->numel, (long long)want);
+      return AT_EINVAL;
+    }
+  }
   tb.n_levels = c.n_levels; tb.T = T; tb.L = L;
   int cum = 0;
   for (int i = 0; i < 8; ++i) { tb.pn[i] = 0; tb.cum[i] = 0; }
@@ -301,6 +308,7 @@ int g_skinny_tokens = 1;        // AR scale steps with at most this many new tok
 int g_pdl_mask = 3;            // measured in the chunk graph: GEMM/attention edges help (-3.4 %), elementwise edges cancel it
 int g_pdl_w2v_max_chunks = 1 << 30;
 int g_w2v_graph_chunks = 4;     // option "w2v_graph_chunks": wav2vec calls with at most this many chunks replay a CUDA graph
+int g_posconv4 = 1;            // option "posconv4": bf16 mode runs the positional conv in its four-frames-per-row form (posconv_tc.cu)
 int g_attn_bound = 1;          // option "attn_bound": AR attention subtracts the per-head score bound instead of the row maximum
 
 // ------------------------------------------------------------------ launch trace
@@ -408,6 +416,13 @@ int Engine::attention(const AttnArgs& a, cudaStream_t st) {
   PROF_WRAP(1, 4.0 * a.n_seq * a.n_heads * a.head_dim * a.lq * keys, a.n_seq * a.n_heads, a.lq, a.lk, launch_attention(a, st));
 }
 
+int Engine::posconv4(const void* x, const void* w4, const float* bias, const float* resid, float* out, int n, cudaStream_t st) {
+  const EngineConfig& c = cfg;
+  const int G = c.w2v_pos_groups, H = c.w2v_hidden, F = n_audio_frames;
+  PROF_WRAP(0, 2.0 * n * F * H * (double)(H / G) * c.w2v_pos_kernel, n * F, H, c.w2v_pos_kernel * (H / G),
+            launch_posconv4(x, w4, bias, resid, out, n, F, H, G, c.w2v_pos_kernel, st));
+}
+
 // ------------------------------------------------------------------ wav2vec2
 size_t Engine::audio_ws_per_chunk() const {
   const size_t s = dt_size(act_dt());
@@ -494,7 +509,12 @@ int Engine::audio_encode_sub(const float* audio, int n, float* cond, cudaStream_
     AT_TRY(gemm(g, st));
   }
   // positional conv embedding: grouped conv k=128 pad 64 (last output dropped) + GELU + residual (:360-368,764-765)
-  {
+  const Tensor* w4 = (c.precision == 1 && g_posconv4) ? find("w2v.pos.w4") : nullptr;
+  if (w4 && posconv4_supported(F, H, c.w2v_pos_groups, c.w2v_pos_kernel)) {
+    // bf16 mode: four output frames per A row, N = 256 pair tiles (posconv_tc.cu); bit-identical to the tap-mode GEMM below
+    AT_TRY(posconv4(bufA, w4->ptr, get<float>("w2v.pos.b"), h, h2, n, st));
+    std::swap(h, h2);
+  } else {
     const int G = c.w2v_pos_groups, gw = H / G;
     GemmArgs g = gemm_args();
     g.A = (adt == DT_F32) ? (const void*)h : (const void*)bufA;

@@ -59,6 +59,7 @@ struct Engine {
 
   int gemm(const GemmArgs& g, cudaStream_t st);
   int attention(const AttnArgs& a, cudaStream_t st);
+  int posconv4(const void* x, const void* w4, const float* bias, const float* resid, float* out, int n, cudaStream_t st);
   // optional CUDA-event instrumentation of the GEMM / attention launches (bench.py roofline pass)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev; std::vector<double> prof_flops; std::vector<int> prof_cls; std::vector<std::array<int, 3>> prof_dims;

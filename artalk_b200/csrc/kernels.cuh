@@ -90,6 +90,14 @@ bool gemm_skinny_supported(const GemmArgs& g);
 int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st);
 void set_skinny_max_m(int v);
 
+// ---------------- posconv_tc.cu ----------------
+// wav2vec2 positional conv (16 groups x 64 channels, 128 taps, pad 64) + bias + GELU + residual as a CTA-pair tcgen05 GEMM with
+// four output frames per A row (N = 256). x [n_chunks][F][H] bf16, w4 [groups][256][(taps + 3) * 64] bf16 (weights.repack
+// "w2v.pos.w4"), resid / out [n_chunks * F][H] fp32 (may not alias).
+bool posconv4_supported(int F, int H, int groups, int taps);
+int launch_posconv4(const void* x, const void* w4, const float* bias, const float* resid, float* out, int n_chunks, int F, int H,
+                    int groups, int taps, cudaStream_t st);
+
 // ---------------- split.cu ----------------
 // fp32 [n_elems] -> bf16 piece blocks [n_elems / 64][slots][64] (slots 3: 2 pieces / 3 MMA passes, 6: 3 pieces / 6 passes);
 // is_w selects the weight-side slot order so that slot s of A times slot s of W enumerates the kept piece products

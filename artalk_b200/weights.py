@@ -76,6 +76,18 @@ def savgol_hat(window: int, poly: int) -> np.ndarray:
     return (V @ np.linalg.pinv(V)).astype(np.float32)
 
 
+def posconv_shift4(pw: torch.Tensor, groups: int) -> torch.Tensor:
+    """Positional-conv weight (hidden, hidden / groups, taps) -> the four-frames-per-row operand of csrc/posconv_tc.cu:
+    B'[g][s*gw + co][j'*gw + ci] = W[g*gw + co][ci][j' - s] for the four frame shifts s, j' in [0, taps + 3), zero where j' - s
+    falls outside the kernel (out[4t'+s] = sum_j' B'[s][j'] x[4t' + j' - taps/2])."""
+    H, gw, K = pw.shape
+    src = pw.view(groups, H // groups, gw, K).permute(0, 1, 3, 2)                   # [g][co][j][ci]
+    w4 = torch.zeros(groups, 4, H // groups, K + 3, gw, dtype=pw.dtype, device=pw.device)
+    for s in range(4):
+        w4[:, s, :, s:s + K, :] = src
+    return w4.reshape(groups, 4 * (H // groups), (K + 3) * gw)
+
+
 def repack(sd: Dict[str, torch.Tensor], cfg: ModelConfig, device, precision: str) -> Dict[str, torch.Tensor]:
     """reference state_dict -> {canonical name: contiguous device tensor}."""
     validate_state_dict(sd, cfg)
@@ -110,6 +122,8 @@ def repack(sd: Dict[str, torch.Tensor], cfg: ModelConfig, device, precision: str
     pw = pg * pv / pv.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()                  # (1024, 64, 128)
     G, gw, K = w.pos_conv_groups, H // w.pos_conv_groups, w.pos_conv_kernel
     put("w2v.pos.w", pw.view(G, gw, gw, K).permute(0, 1, 3, 2).reshape(G, gw, K * gw), wt)   # [g][out][tap*in]
+    if precision == "bf16" and gw == 64 and K == 128:
+        put("w2v.pos.w4", posconv_shift4(pw, G), wt)
     put("w2v.pos.b", g(a + "encoder.pos_conv_embed.conv.bias"))
     put("w2v.enc_ln_g", g(a + "encoder.layer_norm.weight"))
     put("w2v.enc_ln_b", g(a + "encoder.layer_norm.bias"))

@@ -225,6 +225,12 @@ typedef struct artalk_attn {
 int artalk_op_attention(const artalk_attn_t* a, void* stream);
 int artalk_op_layernorm(const float* x, void* out, int out_dt, const float* gamma, const float* beta, int rows, int cols,
                         float eps, int act, void* stream);
+/* wav2vec2 positional conv of the bf16 path (transformers modeling_wav2vec2.py:360-368,764-765: grouped Conv1d k=128 pad 64,
+ * last output dropped, + bias, GELU, + residual) in its four-frames-per-row tensor-core form: x [n_chunks][frames][hidden]
+ * bf16, w4 [groups][256][(taps + 3) * 64] bf16 (artalk_b200.weights.posconv_shift4), bias [hidden], resid / out
+ * [n_chunks * frames][hidden] f32 (distinct buffers). hidden = groups * 64, taps = 128. */
+int artalk_op_posconv4(const void* x, const void* w4, const float* bias, const float* resid, float* out, int n_chunks, int frames,
+                       int hidden, int groups, int taps, void* stream);
 
 #ifdef __cplusplus
 }

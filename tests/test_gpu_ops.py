@@ -272,6 +272,38 @@ def test_pos_conv_grouped_tap_gemm(pname, prec, dt, tol):
     assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("n", [1, 2, 5, 11])
+def test_pos_conv_four_frames_per_row(n):
+    """posconv_tc.cu: the positional conv with four output frames per A row (N = 256 CTA-pair tiles, shifted filter copies from
+    weights.posconv_shift4). Same products in the same tap order as the N = 64 tap-mode GEMM (the added ones are exact zeros):
+    bit-identical to it, and within the bf16 tolerance of the fp64 reference; chunk counts that leave the last CTA / tile partly
+    or wholly out of range (1, 2, 5) and more than one tile (11)."""
+    from artalk_b200 import weights
+    Fr, H, G, K = 199, 1024, 16, 128
+    gw = H // G
+    g = torch.Generator(device="cpu").manual_seed(17 + n)
+    h = torch.randn(n, Fr, H, generator=g).to(dev())
+    w = (torch.randn(H, gw, K, generator=g) / math.sqrt(gw * K)).to(dev())
+    b = torch.randn(H, generator=g).to(dev())
+    A = h.to(torch.bfloat16)
+    w4 = weights.posconv_shift4(w, G).to(torch.bfloat16).contiguous()
+    assert w4.shape == (G, 256, (K + 3) * gw)
+    out = torch.full((n * Fr, H), float("nan"), device=dev())
+    _lib.check(_lib.lib().artalk_op_posconv4(A.data_ptr(), w4.data_ptr(), b.data_ptr(), h.data_ptr(), out.data_ptr(), n, Fr, H, G, K,
+                                             _lib.stream_ptr(dev())))
+    torch.cuda.synchronize()
+    pc = F.conv1d(A.double().transpose(1, 2), w.to(torch.bfloat16).double(), b.double(), padding=K // 2, groups=G)[:, :, :-1]
+    ref = (h.double() + F.gelu(pc).transpose(1, 2)).reshape(n * Fr, H).float()
+    assert bool(torch.isfinite(out).all())
+    assert (out - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    wp = w.view(G, gw, gw, K).permute(0, 1, 3, 2).reshape(G, gw, K * gw).contiguous().to(torch.bfloat16)
+    old = torch.empty(n * Fr, H, device=dev())
+    run_gemm(1, A, wp, n * Fr, gw, K * gw, a_map=rowmap(Fr, Fr * H, H), tap_w=gw, tap_pad=K // 2, groups=G, a_gs=gw,
+             w_gs=gw * K * gw, c_gs=gw, bias_gs=gw, bias=b, act=1, resid=h.view(-1, H), resid_map=rowmap(0, 0, H),
+             out32=old, c_map=rowmap(0, 0, H), ldw=K * gw)
+    assert torch.equal(out, old)
+
+
 # ----------------------------------------------------------------------------- parity-grade tensor-core mode (split.cu)
 def split_op(x, slots, is_w):
     """fp32 tensor -> bf16 piece blocks [numel / 64][slots][64] through artalk_op_split_bf16."""

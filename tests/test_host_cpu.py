@@ -121,6 +121,15 @@ def test_repack_algebra_cpu():
     win = win.view(1, 40, 16, 64, 128).permute(0, 1, 2, 4, 3).reshape(1, 40, 16, 128 * 64)
     mine = torch.einsum("btgk,gok->btgo", win, t["w2v.pos.w"]).reshape(1, 40, 1024)
     assert torch.allclose(mine, ref, atol=1e-4)
+    # the same conv with four output frames per operand row (csrc/posconv_tc.cu): A'[t'][j'] = x[4t' + j' - 64] against the four
+    # shifted filter copies of weights.posconv_shift4 gives out[4t' + s] in column block s
+    w4 = W.posconv_shift4(wn, 16)                                       # (16, 256, 131 * 64)
+    hp4 = F.pad(h, (0, 0, 64, 67 + 3))                                  # frames -64 .. 40 + 69
+    a4 = torch.stack([hp4[0, 4 * tp:4 * tp + 131] for tp in range(10)])  # (10, 131, 1024): [t'][j'][c]
+    a4 = a4.view(10, 131, 16, 64).permute(0, 2, 1, 3).reshape(10, 16, 131 * 64)
+    o4 = torch.einsum("tgk,gnk->tgn", a4, w4).view(10, 16, 4, 64)       # [t'][g][s][co]
+    mine4 = o4.permute(0, 2, 1, 3).reshape(1, 40, 1024)                 # frame 4t' + s, channel g * 64 + co
+    assert torch.allclose(mine4, ref, atol=1e-4)
     # conv layer 1 in channels-last implicit-GEMM form
     x = torch.randn(1, 512, 21)
     ref = F.conv1d(x, sd["audio_encoder.feature_extractor.conv_layers.1.conv.weight"], None, stride=2)
