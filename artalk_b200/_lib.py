@@ -114,6 +114,7 @@ SYMBOLS = {
     "artalk_op_attention": (C.c_int, [C.POINTER(Attn), C.c_void_p]),
     "artalk_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_float, C.c_int, C.c_void_p]),
+    "artalk_op_conv0": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_float, C.c_void_p]),
     "artalk_op_posconv4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p]),
 }
@@ -154,6 +155,8 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"skinny_max_m", int(os.environ["ARTALK_SKINNY_MAX_M"]))
         if os.environ.get("ARTALK_ATTN_BOUND"):            # 0: AR attention keeps the max pass (A/B switch)
             l.artalk_set_option(b"attn_bound", int(os.environ["ARTALK_ATTN_BOUND"]))
+        if os.environ.get("ARTALK_CONV0_FOLD"):            # 0: conv layer 0 in its direct form (A/B switch)
+            l.artalk_set_option(b"conv0_fold", int(os.environ["ARTALK_CONV0_FOLD"]))
         if os.environ.get("ARTALK_POSCONV4"):              # 0: positional conv as the N = 64 tap-mode GEMM (A/B switch)
             l.artalk_set_option(b"posconv4", int(os.environ["ARTALK_POSCONV4"]))
         if os.environ.get("ARTALK_ATTN_POLY"):

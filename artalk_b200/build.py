@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libartalk_b200.so")
-SOURCES = ["norms.cu", "gemm_simt.cu", "gemm_tc.cu", "skinny.cu", "split.cu", "attention.cu", "attention_tc.cu", "posconv_tc.cu", "bits.cu", "flame.cu", "flame_tc.cu", "postproc.cu", "mesh.cu", "frontend.cu",
+SOURCES = ["norms.cu", "gemm_simt.cu", "gemm_tc.cu", "skinny.cu", "split.cu", "attention.cu", "attention_tc.cu", "posconv_tc.cu", "conv0_fold.cu", "bits.cu", "flame.cu", "flame_tc.cu", "postproc.cu", "mesh.cu", "frontend.cu",
            "engine.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

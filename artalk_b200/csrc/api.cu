@@ -193,6 +193,8 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "skinny_tokens")) { g_skinny_tokens = value; return AT_OK; }
   if (!std::strcmp(name, "attn_bound")) { g_attn_bound = value; return AT_OK; }
   if (!std::strcmp(name, "posconv4")) { g_posconv4 = value; return AT_OK; }
+  if (!std::strcmp(name, "conv0_fold")) { g_conv0_fold = value; return AT_OK; }
+  if (!std::strcmp(name, "ar_defer_max")) { g_ar_defer_max = value; return AT_OK; }
   if (!std::strcmp(name, "attn_poly")) { set_attn_poly(value); return AT_OK; }
   if (!std::strcmp(name, "w2v_graph_chunks")) { g_w2v_graph_chunks = value; return AT_OK; }
   if (!std::strcmp(name, "skinny_max_m")) { set_skinny_max_m(value); return AT_OK; }
@@ -242,6 +244,21 @@ int artalk_op_posconv4(const void* x, const void* w4, const float* bias, const f
                        int hidden, int groups, int taps, void* stream) {
   AT_REQUIRE(x && w4 && bias && resid && out && resid != out, "null or aliased argument");
   return launch_posconv4(x, w4, bias, resid, out, n_chunks, frames, hidden, groups, taps, (cudaStream_t)stream);
+}
+
+int artalk_op_conv0(const float* audio, int n_chunks, int n_samples, const float* w_kc, const float* bias, const float* ln_g,
+                    const float* ln_b, const float* wq, const float* bq, const float* qf, float* stats_ws, void* out, int out_dt,
+                    float eps, void* stream) {
+  AT_REQUIRE(audio && ln_b && stats_ws && out && n_samples >= 10, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int l_out = (n_samples - 10) / 5 + 1;
+  AT_TRY(launch_audio_stats(audio, n_chunks, n_samples, (float2*)stats_ws, st));
+  if (wq) {
+    AT_REQUIRE(bq && qf && out_dt == DT_BF16, "conv0: the folded form needs wq, bq, qf and a bf16 output");
+    return launch_conv0_fold(audio, (const float2*)stats_ws, wq, bq, ln_b, qf, out, n_chunks, n_samples, l_out, eps, st);
+  }
+  AT_REQUIRE(w_kc && bias && ln_g, "null argument");
+  return launch_conv0_ln_gelu(audio, (const float2*)stats_ws, w_kc, bias, ln_g, ln_b, out, out_dt, n_chunks, n_samples, l_out, 10, 5, eps, st);
 }
 
 int artalk_op_layernorm(const float* x, void* out, int out_dt, const float* gamma, const float* beta, int rows, int cols,

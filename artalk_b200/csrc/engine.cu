@@ -147,6 +147,16 @@ int Engine::finalize() {
       return AT_EINVAL;
     }
   }
+  {                                                 // optional: folded conv layer 0 operands (bf16 mode)
+    const Tensor* qf = find("w2v.conv0.qf"); const Tensor* wq = find("w2v.conv0.wq"); const Tensor* bq = find("w2v.conv0.bq");
+    if (qf || wq || bq) {
+      if (!(qf && wq && bq) || qf->dt != DT_F32 || wq->dt != DT_F32 || bq->dt != DT_F32 || qf->numel != 11 * 12 || wq->numel != 10 * (int64_t)CD ||
+          bq->numel != CD || CD != 512) {
+        set_last_error("finalize: 'w2v.conv0.wq' [10][512] / 'w2v.conv0.bq' [512] / 'w2v.conv0.qf' [11][12] (f32) must be given together");
+        return AT_EINVAL;
+      }
+    }
+  }
   if (const Tensor* w4 = find("w2v.pos.w4")) {      // optional: shifted filter copies of the positional conv (bf16 mode)
     const int64_t want = (int64_t)c.w2v_pos_groups * 256 * (c.w2v_pos_kernel + 3) * 64;
     if (w4->dt != DT_BF16 || w4->numel != want) {
@@ -308,6 +318,8 @@ int g_skinny_tokens = 1;        // AR scale steps with at most this many new tok
 int g_pdl_mask = 3;            // measured in the chunk graph: GEMM/attention edges help (-3.4 %), elementwise edges cancel it
 int g_pdl_w2v_max_chunks = 1 << 30;
 int g_w2v_graph_chunks = 4;     // option "w2v_graph_chunks": wav2vec calls with at most this many chunks replay a CUDA graph
+int g_ar_defer_max = 1 << 20;  // option "ar_defer_max": scale steps with more new tokens per clip fuse the gated residual into the GEMM epilogue
+int g_conv0_fold = 1;          // option "conv0_fold": bf16 mode runs conv layer 0 with the LayerNorm folded through the conv (conv0_fold.cu)
 int g_posconv4 = 1;            // option "posconv4": bf16 mode runs the positional conv in its four-frames-per-row form (posconv_tc.cu)
 int g_attn_bound = 1;          // option "attn_bound": AR attention subtracts the per-head score bound instead of the row maximum
 
@@ -478,9 +490,15 @@ int Engine::audio_encode_sub(const float* audio, int n, float* cond, cudaStream_
   WS(h2, float*, (size_t)M * H * 4);
 
   AT_TRY(launch_audio_stats(audio, n, c.chunk_samples, stats, st));
-  AT_TRY(launch_conv0_ln_gelu(audio, stats, get<float>("w2v.conv0.w"), get<float>("w2v.conv0.b"), get<float>("w2v.conv0.ln_g"),
-                              get<float>("w2v.conv0.ln_b"), bufA, adt, n, c.chunk_samples, conv_len[0], c.w2v_conv_kernel[0],
-                              c.w2v_conv_stride[0], c.w2v_ln_eps, st));
+  const Tensor* c0q = (c.precision == 1 && g_conv0_fold && c.w2v_conv_kernel[0] == 10 && c.w2v_conv_stride[0] == 5) ? find("w2v.conv0.qf") : nullptr;
+  if (c0q && find("w2v.conv0.wq") && find("w2v.conv0.bq"))
+    // bf16 mode: LayerNorm statistics from the frame's samples (quadratic form), filters in registers, packed FMAs (conv0_fold.cu)
+    AT_TRY(launch_conv0_fold(audio, stats, get<float>("w2v.conv0.wq"), get<float>("w2v.conv0.bq"), get<float>("w2v.conv0.ln_b"),
+                             (const float*)c0q->ptr, bufA, n, c.chunk_samples, conv_len[0], c.w2v_ln_eps, st));
+  else
+    AT_TRY(launch_conv0_ln_gelu(audio, stats, get<float>("w2v.conv0.w"), get<float>("w2v.conv0.b"), get<float>("w2v.conv0.ln_g"),
+                                get<float>("w2v.conv0.ln_b"), bufA, adt, n, c.chunk_samples, conv_len[0], c.w2v_conv_kernel[0],
+                                c.w2v_conv_stride[0], c.w2v_ln_eps, st));
   char* in = bufA; char* out = bufB;
   for (int i = 1; i < c.w2v_n_conv; ++i) {
     // implicit GEMM: row t of the A operand is the contiguous window in[t*stride : t*stride + k][:] of the
@@ -873,9 +891,9 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
   WS(f, char*, (size_t)B * Tm * 4 * C * s);
   // bf16 mode: the projection / FFN2 GEMMs write y = A W^T + b (fp32) with the plain epilogue and the gated residual update
   // x += gamma * y is folded into the next AdaLN kernel (bit-identical, see norms.cu); fp32 mode keeps the fused epilogue
-  const bool defer = (adt == DT_BF16);
+  const bool defer_ok = (adt == DT_BF16);
   float* ybuf = nullptr;
-  if (defer) { ybuf = (float*)ws_alloc((size_t)B * Tm * C * 4); if (!ybuf) return AT_ENOMEM; }
+  if (defer_ok) { ybuf = (float*)ws_alloc((size_t)B * Tm * C * 4); if (!ybuf) return AT_ENOMEM; }
 
   // AdaLN parameters of every block + head for all 181 tokens, once per chunk (audio-only)
   GemmArgs g = gemm_args();
@@ -904,6 +922,7 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
   for (int p = 0; p < c.n_levels; ++p) {
     const int n_new = c.patch_nums[p], off = p ? tb.cum[p - 1] : 0, M = B * n_new;
     const int sk = n_new <= g_skinny_tokens ? 1 : 0;           // per-clip criterion: batch-size independent arithmetic
+    const bool defer = defer_ok && n_new <= g_ar_defer_max;   // (deferred and fused gated-residual updates are bit-identical)
     const RowMap ada_map = batched_rows(n_new, (int64_t)L * n_ada, n_ada);
     const char* ada_p = ada + (size_t)off * n_ada * s;
     const uint32_t* src_words = forced_words ? forced_words : words;

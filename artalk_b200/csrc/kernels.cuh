@@ -90,6 +90,12 @@ bool gemm_skinny_supported(const GemmArgs& g);
 int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st);
 void set_skinny_max_m(int v);
 
+// ---------------- conv0_fold.cu ----------------
+// bf16 path of conv layer 0 with the LayerNorm folded through the convolution (statistics from the frame's 10 samples, packed
+// FFMA2 arithmetic). wq [10][512], bq [512], beta [512], qf [11][12] from weights.conv0_fold; out bf16 [n_chunks][l_out][512]
+int launch_conv0_fold(const float* audio, const float2* stats, const float* wq, const float* bq, const float* beta, const float* qf,
+                      void* out, int n_chunks, int n_samples, int l_out, float eps, cudaStream_t st);
+
 // ---------------- posconv_tc.cu ----------------
 // wav2vec2 positional conv (16 groups x 64 channels, 128 taps, pad 64) + bias + GELU + residual as a CTA-pair tcgen05 GEMM with
 // four output frames per A row (N = 256). x [n_chunks][F][H] bf16, w4 [groups][256][(taps + 3) * 64] bf16 (weights.repack

@@ -76,6 +76,21 @@ def savgol_hat(window: int, poly: int) -> np.ndarray:
     return (V @ np.linalg.pinv(V)).astype(np.float32)
 
 
+def conv0_fold(cw: torch.Tensor, b: torch.Tensor, g: torch.Tensor):
+    """Conv layer 0 (512, 10) + LayerNorm(512) folded (csrc/conv0_fold.cu): with wc = w - mean_c(w), bc = b - mean_c(b) the
+    centred conv output is wc.x + bc and its variance over channels is [x;1]^T Q [x;1], Q = Z^T Z / 512, Z = [wc | bc].
+    Returns wq [10][512] = (wc * gamma)^T, bq [512] = bc * gamma and qf [11][12]: rows sqrt(lambda_i) v_i of Q's
+    eigen-decomposition (fp64), so that var = sum_i (qf_i . [x;1])^2; column 11 is padding."""
+    cw64, b64, g64 = cw.double(), b.double(), g.double()
+    wc = cw64 - cw64.mean(0, keepdim=True)
+    bc = b64 - b64.mean()
+    z = torch.cat([wc, bc[:, None]], 1)                                         # (512, 11)
+    lam, vec = torch.linalg.eigh(z.t() @ z / z.shape[0])
+    qf = torch.zeros(11, 12, dtype=torch.float64)
+    qf[:, :11] = (vec * lam.clamp_min(0).sqrt()[None, :]).t()
+    return (wc * g64[:, None]).t().contiguous().float(), (bc * g64).float(), qf.float()
+
+
 def posconv_shift4(pw: torch.Tensor, groups: int) -> torch.Tensor:
     """Positional-conv weight (hidden, hidden / groups, taps) -> the four-frames-per-row operand of csrc/posconv_tc.cu:
     B'[g][s*gw + co][j'*gw + ci] = W[g*gw + co][ci][j' - s] for the four frame shifts s, j' in [0, taps + 3), zero where j' - s
@@ -110,6 +125,9 @@ def repack(sd: Dict[str, torch.Tensor], cfg: ModelConfig, device, precision: str
             put("w2v.conv0.w", cw[:, 0, :].t())                                   # [k][512]
         else:
             put("w2v.conv%d.w" % i, cw.permute(0, 2, 1).reshape(CD, k * CD), wt)      # [Cout][tap*Cin]
+        if i == 0 and precision == "bf16" and k == 10 and w.conv_stride[0] == 5 and CD == 512:
+            wq, bq, qf = conv0_fold(cw[:, 0, :], g(p + "conv.bias"), g(p + "layer_norm.weight"))
+            put("w2v.conv0.wq", wq); put("w2v.conv0.bq", bq); put("w2v.conv0.qf", qf)
         put("w2v.conv%d.b" % i, g(p + "conv.bias"))
         put("w2v.conv%d.ln_g" % i, g(p + "layer_norm.weight"))
         put("w2v.conv%d.ln_b" % i, g(p + "layer_norm.bias"))

@@ -225,6 +225,14 @@ typedef struct artalk_attn {
 int artalk_op_attention(const artalk_attn_t* a, void* stream);
 int artalk_op_layernorm(const float* x, void* out, int out_dt, const float* gamma, const float* beta, int rows, int cols,
                         float eps, int act, void* stream);
+/* wav2vec2 feature-extractor layer 0 (modeling_wav2vec2.py:291-299: Conv1d(1, 512, k=10, s=5) + LayerNorm + GELU) on per-chunk
+ * normalised audio (app/modules/wav2vec.py:23-27): audio [n_chunks][n_samples] f32 -> out [n_chunks][(n_samples-10)/5+1][512].
+ * wq == NULL: direct form (w_kc [10][512], bias, ln_g, ln_b; out f32 or bf16). wq != NULL: bf16 path with the LayerNorm folded
+ * through the conv (wq [10][512], bq [512], qf [11][12] from artalk_b200.weights.conv0_fold; ln_b; bf16 out).
+ * stats_ws: 2 * n_chunks floats of scratch. */
+int artalk_op_conv0(const float* audio, int n_chunks, int n_samples, const float* w_kc, const float* bias, const float* ln_g,
+                    const float* ln_b, const float* wq, const float* bq, const float* qf, float* stats_ws, void* out, int out_dt,
+                    float eps, void* stream);
 /* wav2vec2 positional conv of the bf16 path (transformers modeling_wav2vec2.py:360-368,764-765: grouped Conv1d k=128 pad 64,
  * last output dropped, + bias, GELU, + residual) in its four-frames-per-row tensor-core form: x [n_chunks][frames][hidden]
  * bf16, w4 [groups][256][(taps + 3) * 64] bf16 (artalk_b200.weights.posconv_shift4), bias [hidden], resid / out

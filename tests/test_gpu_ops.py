@@ -272,6 +272,44 @@ def test_pos_conv_grouped_tap_gemm(pname, prec, dt, tol):
     assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("n,S", [(1, 64000), (3, 64000), (2, 3212)])
+def test_conv0_layernorm_folded_through_the_conv(n, S):
+    """conv0_fold.cu: conv layer 0 + LayerNorm + GELU with the LayerNorm statistics taken from the frame's 10 samples (quadratic
+    form of the channel-centred filters, weights.conv0_fold) against (a) the fp64 reference and (b) the direct kernel, whose
+    bf16 outputs it must match to within one bf16 step of the GELU output (the two differ in fp32 rounding only). Inputs with a
+    DC offset and a common filter component exercise the centring."""
+    from artalk_b200 import weights
+    g = torch.Generator(device="cpu").manual_seed(5 + n)
+    audio = (0.1 * torch.randn(n, S, generator=g) + 0.05).to(dev())
+    cw = (torch.randn(512, 10, generator=g) * 0.3 + 0.1 * torch.randn(1, 10, generator=g)).to(dev())
+    b = (0.2 * torch.randn(512, generator=g) + 0.1).to(dev())
+    lg = (1.0 + 0.2 * torch.randn(512, generator=g)).to(dev())
+    lb = (0.1 * torch.randn(512, generator=g)).to(dev())
+    wq, bq, qf = [t.to(dev()).contiguous() for t in weights.conv0_fold(cw.cpu(), b.cpu(), lg.cpu())]
+    L = (S - 10) // 5 + 1
+    ws = torch.empty(2 * n, device=dev())
+    w_kc = cw.t().contiguous()
+    outs = []
+    for fold in (False, True):
+        out = torch.full((n, L, 512), float("nan"), device=dev(), dtype=torch.bfloat16)
+        _lib.check(_lib.lib().artalk_op_conv0(audio.data_ptr(), n, S, w_kc.data_ptr(), b.data_ptr(), lg.data_ptr(), lb.data_ptr(),
+                                              wq.data_ptr() if fold else None, bq.data_ptr() if fold else None,
+                                              qf.data_ptr() if fold else None, ws.data_ptr(), out.data_ptr(), _lib.BF16, 1e-5,
+                                              _lib.stream_ptr(dev())))
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(out.float()).all())
+        outs.append(out.float())
+    a64 = audio.double()
+    xn = (a64 - a64.mean(1, keepdim=True)) / (a64.std(1, keepdim=True) + 1e-6)          # app/modules/wav2vec.py:23-27
+    y = F.conv1d(xn[:, None, :], cw.double()[:, None, :], b.double(), stride=5).transpose(1, 2)
+    ref = F.gelu(F.layer_norm(y, (512,), lg.double(), lb.double(), 1e-5)).float()
+    for o in outs:
+        assert (o - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    d = (outs[0] - outs[1]).abs()
+    assert d.max().item() <= 2.0 ** -7 * max(1.0, ref.abs().max().item())      # at most one bf16 step of the largest output
+    assert (d > 0).float().mean().item() < 0.05                                 # and only where the fp32 value sat on a rounding boundary
+
+
 @pytest.mark.parametrize("n", [1, 2, 5, 11])
 def test_pos_conv_four_frames_per_row(n):
     """posconv_tc.cu: the positional conv with four output frames per A row (N = 256 CTA-pair tiles, shifted filter copies from

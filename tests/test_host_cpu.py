@@ -130,6 +130,16 @@ def test_repack_algebra_cpu():
     o4 = torch.einsum("tgk,gnk->tgn", a4, w4).view(10, 16, 4, 64)       # [t'][g][s][co]
     mine4 = o4.permute(0, 2, 1, 3).reshape(1, 40, 1024)                 # frame 4t' + s, channel g * 64 + co
     assert torch.allclose(mine4, ref, atol=1e-4)
+    # conv layer 0 with the LayerNorm folded through the conv (csrc/conv0_fold.cu): centred filters + quadratic-form variance
+    cw0, b0 = sd["audio_encoder.feature_extractor.conv_layers.0.conv.weight"][:, 0, :], sd["audio_encoder.feature_extractor.conv_layers.0.conv.bias"]
+    g0, be0 = sd["audio_encoder.feature_extractor.conv_layers.0.layer_norm.weight"], sd["audio_encoder.feature_extractor.conv_layers.0.layer_norm.bias"]
+    wq, bq, qf = W.conv0_fold(cw0, b0, g0)
+    xa = torch.randn(37, 10) + 0.3
+    ref0 = F.layer_norm(xa @ cw0.t() + b0, (512,), g0, be0, 1e-5)
+    z = torch.cat([xa, torch.ones(37, 1)], 1)
+    var = ((z @ qf[:, :11].t()) ** 2).sum(1, keepdim=True)
+    mine0 = (xa @ wq + bq) * torch.rsqrt(var + 1e-5) + be0
+    assert torch.allclose(mine0, ref0, atol=2e-5)
     # conv layer 1 in channels-last implicit-GEMM form
     x = torch.randn(1, 512, 21)
     ref = F.conv1d(x, sd["audio_encoder.feature_extractor.conv_layers.1.conv.weight"], None, stride=2)
