@@ -384,6 +384,287 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------- block-wise kernel: 256 < keys <= 384 (the caller gives score bounds)
+// The AR steps of the two finest scales see 262 / 362 keys: S no longer fits one 256-column buffer, and the split-key mode above
+// puts BOTH warpgroups on one item, so the chain MMA1 -> softmax -> MMA2 -> epilogue of an item runs with nothing else in flight
+// (6.5 us per item measured against 2.6 us of TMEM traffic). With bounded scores (|q.k| <= head_scale, no row maximum) the keys
+// can be consumed in two independent blocks of <= 192: S_blk = Q K_blk^T -> P_blk = exp2(S_blk - bound) -> O += P_blk V_blk, the
+// row sum simply accumulates (a head whose bound is too large to use falls back to an online softmax over the two blocks, with
+// the usual rescaling of sum and O). So each warpgroup keeps its own item and 256-column buffer (S_blk in [0, 192), P_blk over the
+// S columns already read, O in [192, 256)) as in ping-pong mode: two item chains in flight per SM.
+//   * K / V arrive per block in a ring of four 48 KB stages (two per warpgroup), Q in one 16 KB slot per warpgroup, so the next
+//     item's first block loads while the current item's second block is processed;
+//   * one MMA issuer thread per buffer (warps 1 and 3): neither item's chain ever waits behind the other's barriers;
+//   * P_blk0 is read by MMA 2 from the columns MMA 1 of block 1 overwrites: the issuer waits for MMA 2 (block 0) to complete
+//     (tcgen05.commit on a private barrier) before it issues MMA 1 (block 1) - different accumulators are not ordered otherwise.
+constexpr int BLK_MAX = 192;                      // keys per block
+constexpr int KVB_BYTES = BLK_MAX * 128;          // K (or V) rows of one block stage
+constexpr int BSTAGE_BYTES = 2 * KVB_BYTES;       // K block | V block
+constexpr int BLK_O_COL = 192;
+constexpr int SMEM_BLK = 4 * BSTAGE_BYTES + 2 * Q_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(SMEM_BLK <= SMEM_LIMIT, "attn_blk: shared memory budget");
+
+__global__ void __launch_bounds__(384, 1)
+attn_blk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
+                const __grid_constant__ CUtensorMap tmV2, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_base = smem_base + 4 * BSTAGE_BYTES;
+  const uint32_t bar_base = q_base + 2 * Q_BYTES;
+  // barriers (8 B each): kv_full[4], kv_empty[4], then per buffer q_full, q_empty, s_full, p_full, o_full, s_empty, pv_done
+  auto kv_full = [&](int s) { return bar_base + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto q_full = [&](int b) { return bar_base + 8u * (8 + b); };
+  auto q_empty = [&](int b) { return bar_base + 8u * (10 + b); };
+  auto s_full = [&](int b) { return bar_base + 8u * (12 + b); };
+  auto p_full = [&](int b) { return bar_base + 8u * (14 + b); };
+  auto o_full = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto s_empty = [&](int b) { return bar_base + 8u * (18 + b); };
+  auto pv_done = [&](int b) { return bar_base + 8u * (20 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 22;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmK2); prefetch_tensormap(&tmV2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(q_full(b), 1); mbar_init(q_empty(b), 1); mbar_init(s_full(b), 1); mbar_init(p_full(b), 4); mbar_init(o_full(b), 1);
+      mbar_init(s_empty(b), 4); mbar_init(pv_done(b), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_launch_dependents();
+
+  const int n_local = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int h1 = p.lk_pad - p.h0;
+
+  if (warp == 0 || warp == 2) {
+    // ===================== TMA producer of buffer b (one thread per buffer: neither waits behind the other's stages) =====
+    // Order per item: block 0 (its stage frees after MMA 2 of the previous item's block 0), Q (frees after MMA 1 of the previous
+    // item's block 1), block 1: every load of the next item is requested as early as its shared memory allows
+    if (lane == 0) {
+      const int b = warp == 0 ? 0 : 1;
+      pdl_wait();
+      for (int it = b; it < n_local; it += 2) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int qt = item % p.q_tiles, sh = item / p.q_tiles, h = sh % p.n_heads, seq = sh / p.n_heads;
+        const uint32_t par = (uint32_t)(it >> 1) & 1u;
+        for (int blk = 0; blk < 2; ++blk) {
+          const int st = 2 * b + blk, nk = blk ? h1 : p.h0, k0 = blk ? p.h0 : 0;
+          mbar_wait(kv_empty(st), par ^ 1u, p.err_flag, 0xA77B0002u);
+          mbar_arrive_expect_tx(kv_full(st), (uint32_t)(2 * nk * 128));
+          const uint32_t sk = smem_base + (uint32_t)(st * BSTAGE_BYTES), sv = sk + KVB_BYTES;
+          tma_load_3d(sk, blk ? &tmK2 : &tmK, kv_full(st), h * 64, k0, seq);
+          tma_load_3d(sv, blk ? &tmV2 : &tmV, kv_full(st), h * 64, k0, seq);
+          if (blk == 0) {
+            mbar_wait(q_empty(b), par ^ 1u, p.err_flag, 0xA77B0001u);
+            mbar_arrive_expect_tx(q_full(b), (uint32_t)Q_BYTES);
+            tma_load_3d(q_base + (uint32_t)(b * Q_BYTES), &tmQ, q_full(b), h * 64, qt * QT, seq);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuer of buffer b =====================
+    if (lane == 0) {
+      const int b = warp == 1 ? 0 : 1;
+      const uint32_t idesc_pv = idesc(64, 1);
+      const uint32_t tb = tmem + (uint32_t)(b * BUF_COLS);
+      const uint64_t dq = desc_kmajor_sw128(q_base + (uint32_t)(b * Q_BYTES));
+      uint32_t c = 0;                                              // block uses of this buffer (s_full / p_full / pv_done phases)
+      for (int it = b; it < n_local; it += 2) {
+        const uint32_t par = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(q_full(b), par, p.err_flag, 0xA77B0003u);
+        mbar_wait(s_empty(b), par ^ 1u, p.err_flag, 0xA77B0004u);      // O of this buffer's previous item has been read
+        for (int blk = 0; blk < 2; ++blk, ++c) {
+          const int st = 2 * b + blk, nk = blk ? h1 : p.h0;
+          mbar_wait(kv_full(st), par, p.err_flag, 0xA77B0005u);
+          tc_fence_after();
+          const uint32_t sk = smem_base + (uint32_t)(st * BSTAGE_BYTES), sv = sk + KVB_BYTES;
+          const uint64_t dk = desc_kmajor_sw128(sk), dv = desc_mnmajor(sv);
+          const uint32_t id = idesc(nk, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(tb, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id, k ? 1u : 0u);
+          tc_commit(s_full(b));
+          if (blk == 1) tc_commit(q_empty(b));                       // Q has been read once these MMAs complete
+          mbar_wait(p_full(b), c & 1u, p.err_flag, 0xA77B0006u);
+          tc_fence_after();
+          for (int ks = 0; ks < (nk >> 4); ++ks)
+            mma_ts(tb + (uint32_t)BLK_O_COL, tb + (uint32_t)(ks * 8), dv + (uint64_t)(ks * 128), idesc_pv, (blk == 0 && ks == 0) ? 0u : 1u);
+          tc_commit(kv_empty(st));
+          if (blk == 0) {
+            // MMA 1 of block 1 overwrites the columns these MMAs read P from
+            tc_commit(pv_done(b));
+            mbar_wait(pv_done(b), (uint32_t)(it >> 1) & 1u, p.err_flag, 0xA77B0007u);
+            tc_fence_after();
+          }
+        }
+        tc_commit(o_full(b));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax + epilogue warpgroup b =====================
+    const int b = (warp - 4) >> 2, q = (warp - 4) & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int row = q * 32 + lane;
+    const uint32_t tb = tmem + lane_addr + (uint32_t)(b * BUF_COLS);
+    uint32_t c = 0;
+    pdl_wait();
+    for (int it = b; it < n_local; it += 2) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int qt = item % p.q_tiles, sh = item / p.q_tiles, h = sh % p.n_heads, seq = sh / p.n_heads;
+      const int qi = qt * QT + row;
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      const bool warp_live = (qt * QT + q * 32) < p.lq;
+      // a head takes its bound as the softmax shift if exp2(-2 * bound * log2 e) stays a normal number (bound <= 32); any other
+      // head (the clamp value 100, or no bound given) runs the two blocks as an online softmax: block maximum first, and the
+      // second block rescales the row sum and the O accumulator of the first (item-uniform branch)
+      const float bnd = p.bound ? __ldg(p.bound + h) : 0.f;
+      const bool bounded = bnd > 0.f && bnd <= 32.0f;
+      float ms = bnd * 1.4426950408889634f, m_run = -INFINITY;
+      float sum2[2] = {0.f, 0.f};
+      for (int blk = 0; blk < 2; ++blk, ++c) {
+        const int nk = blk ? h1 : p.h0, k0 = blk ? p.h0 : 0;
+        const int lk_r = min(max(p.lk - k0, 0), nk);
+        const int n16 = warp_live ? ((lk_r + 15) >> 4) : 0, n16_all = warp_live ? (nk >> 4) : 0;
+        mbar_wait(s_full(b), c & 1u, p.err_flag, 0xA77B0008u);
+        tc_fence_after();
+        uint32_t sa[16], sb[16];
+        if (!bounded) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          auto reduce = [&](const uint32_t (&s0)[16], int cc) {
+            const int base = cc * 16;
+            if (base + 16 <= lk_r) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(s0[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (base + j < lk_r) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(s0[j]));
+            }
+          };
+          if (n16 > 0) tmem_ld16_nowait(tb, sa);
+          for (int cc = 0; cc < n16; cc += 2) {
+            tmem_ld_wait();
+            if (cc + 1 < n16) tmem_ld16_nowait(tb + (uint32_t)(cc * 16 + 16), sb);
+            reduce(sa, cc);
+            if (cc + 1 < n16) {
+              tmem_ld_wait();
+              if (cc + 2 < n16) tmem_ld16_nowait(tb + (uint32_t)(cc * 16 + 32), sa);
+              reduce(sb, cc + 1);
+            }
+          }
+          const float m_new = fmaxf(m_run, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          if (blk == 1) {
+            // MMA 2 of block 0 has completed (the issuer waited for it before MMA 1 of this block) and MMA 2 of this block waits
+            // for p_full: O is ours to rescale
+            const float alpha = (m_run == -INFINITY) ? 0.f : ex2((m_run - m_new) * p.scale_log2e);
+            sum2[0] *= alpha; sum2[1] *= alpha;
+            if (warp_live) {
+#pragma unroll 1
+              for (int g16 = 0; g16 < 4; ++g16) {
+                uint32_t o[16];
+                tmem_ld16_nowait(tb + (uint32_t)(BLK_O_COL + g16 * 16), o);
+                tmem_ld_wait();
+                uint32_t lo[8], hi[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { lo[j] = __float_as_uint(__uint_as_float(o[j]) * alpha); hi[j] = __float_as_uint(__uint_as_float(o[8 + j]) * alpha); }
+                tmem_st8(tb + (uint32_t)(BLK_O_COL + g16 * 16), lo);
+                tmem_st8(tb + (uint32_t)(BLK_O_COL + g16 * 16 + 8), hi);
+              }
+            }
+          }
+          m_run = m_new;
+          ms = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2e;
+        }
+        auto emit = [&](const uint32_t (&s0)[16], int cc) {
+          uint32_t pk[8];
+          const int base = cc * 16;
+          if (base + 16 <= lk_r) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float p0 = ex2(fmaf(__uint_as_float(s0[j]), p.scale_log2e, -ms)), p1 = ex2(fmaf(__uint_as_float(s0[j + 1]), p.scale_log2e, -ms));
+              sum2[(j >> 1) & 1] += p0 + p1;
+              __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+              pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float p0 = (base + j < lk_r) ? ex2(fmaf(__uint_as_float(s0[j]), p.scale_log2e, -ms)) : 0.f;
+              const float p1 = (base + j + 1 < lk_r) ? ex2(fmaf(__uint_as_float(s0[j + 1]), p.scale_log2e, -ms)) : 0.f;
+              sum2[(j >> 1) & 1] += p0 + p1;
+              __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+              pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+          }
+          tmem_st8(tb + (uint32_t)(cc * 8), pk);
+        };
+        if (n16 > 0) tmem_ld16_nowait(tb, sa);
+        for (int cc = 0; cc < n16; cc += 2) {
+          tmem_ld_wait();
+          if (cc + 1 < n16) tmem_ld16_nowait(tb + (uint32_t)(cc * 16 + 16), sb);
+          emit(sa, cc);
+          if (cc + 1 < n16) {
+            tmem_ld_wait();
+            if (cc + 2 < n16) tmem_ld16_nowait(tb + (uint32_t)(cc * 16 + 32), sa);
+            emit(sb, cc + 1);
+          }
+        }
+        const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        for (int cc = n16; cc < n16_all; ++cc) tmem_st8(tb + (uint32_t)(cc * 8), zero);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(b));
+      }
+      mbar_wait(o_full(b), par, p.err_flag, 0xA77B0009u);
+      tc_fence_after();
+      const float inv = 1.0f / (sum2[0] + sum2[1]);
+      const uint32_t ob = tb + (uint32_t)BLK_O_COL;
+      uint32_t o0[16], o1[16], o2[16], o3[16];
+      if (warp_live) {
+        tmem_ld16_nowait(ob, o0); tmem_ld16_nowait(ob + 16, o1); tmem_ld16_nowait(ob + 32, o2); tmem_ld16_nowait(ob + 48, o3);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(b));
+      if (warp_live && qi < p.lq) {
+        bf16* orow = p.out + (int64_t)seq * p.o_ss + (int64_t)qi * p.o_rs + h * 64;
+        auto store16 = [&](const uint32_t (&o)[16], int col) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            __nv_bfloat162 e0 = __floats2bfloat162_rn(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+            __nv_bfloat162 e1 = __floats2bfloat162_rn(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+            __nv_bfloat162 e2 = __floats2bfloat162_rn(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+            __nv_bfloat162 e3 = __floats2bfloat162_rn(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+            uint4 v;
+            v.x = *reinterpret_cast<uint32_t*>(&e0); v.y = *reinterpret_cast<uint32_t*>(&e1);
+            v.z = *reinterpret_cast<uint32_t*>(&e2); v.w = *reinterpret_cast<uint32_t*>(&e3);
+            *reinterpret_cast<uint4*>(orow + col + j) = v;
+          }
+        };
+        store16(o0, 0); store16(o1, 16); store16(o2, 32); store16(o3, 48);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512u);
+  }
+}
+
 int make_map(CUtensorMap* m, const void* base, uint64_t width, uint64_t rows, uint64_t seqs, uint64_t rs_bytes, uint64_t ss_bytes,
              uint32_t box_rows) {
   return make_map_bf16_3d(m, base, width, rows, seqs, rs_bytes, ss_bytes, 64, box_rows);
@@ -391,6 +672,8 @@ int make_map(CUtensorMap* m, const void* base, uint64_t width, uint64_t rows, ui
 
 }  // namespace
 
+int g_attn_blk = 1;        // option "attn_blk": bounded AR attention over 257..384 keys takes the block-wise kernel (one item per warpgroup)
+void set_attn_blk(int v) { g_attn_blk = v; }
 int g_attn_poly = 0;       // option "attn_poly": share of the softmax exponentials computed on the FMA pipe (0, 1 = 1/4, 2 = 1/2)
 void set_attn_poly(int v) { g_attn_poly = v < 0 ? 0 : (v > 2 ? 2 : v); }
 
@@ -443,6 +726,13 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)p.n_stages * p.stage_bytes + fixed;
   const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
   g_trace_dims[0] = a.n_seq * a.n_heads; g_trace_dims[1] = a.lq; g_trace_dims[2] = a.lk;
+  if (g_attn_blk && p.split_keys && a.key_bound && a.split == 0) {
+    // two key blocks per item, one item per warpgroup (see attn_blk_kernel); heads without a usable bound run online
+    AT_TRY(ensure_dyn_smem((const void*)attn_blk_kernel, SMEM_BLK));
+    AT_CUDA(launch_k(attn_blk_kernel, dim3(grid), dim3(384), (size_t)SMEM_BLK, st, tmQ, tmK, tmV, tmK2, tmV2, p));
+    AT_LAUNCH_CHECK();
+    return AT_OK;
+  }
   if (g_attn_poly == 2) AT_CUDA(launch_k(attn_tc_kernel<2>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
   else if (g_attn_poly == 1) AT_CUDA(launch_k(attn_tc_kernel<1>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
   else AT_CUDA(launch_k(attn_tc_kernel<0>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));

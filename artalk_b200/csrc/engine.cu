@@ -318,7 +318,6 @@ int g_skinny_tokens = 1;        // AR scale steps with at most this many new tok
 int g_pdl_mask = 3;            // measured in the chunk graph: GEMM/attention edges help (-3.4 %), elementwise edges cancel it
 int g_pdl_w2v_max_chunks = 1 << 30;
 int g_w2v_graph_chunks = 4;     // option "w2v_graph_chunks": wav2vec calls with at most this many chunks replay a CUDA graph
-int g_ar_defer_max = 1 << 20;  // option "ar_defer_max": scale steps with more new tokens per clip fuse the gated residual into the GEMM epilogue
 int g_conv0_fold = 1;          // option "conv0_fold": bf16 mode runs conv layer 0 with the LayerNorm folded through the conv (conv0_fold.cu)
 int g_posconv4 = 1;            // option "posconv4": bf16 mode runs the positional conv in its four-frames-per-row form (posconv_tc.cu)
 int g_attn_bound = 1;          // option "attn_bound": AR attention subtracts the per-head score bound instead of the row maximum
@@ -891,9 +890,9 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
   WS(f, char*, (size_t)B * Tm * 4 * C * s);
   // bf16 mode: the projection / FFN2 GEMMs write y = A W^T + b (fp32) with the plain epilogue and the gated residual update
   // x += gamma * y is folded into the next AdaLN kernel (bit-identical, see norms.cu); fp32 mode keeps the fused epilogue
-  const bool defer_ok = (adt == DT_BF16);
+  const bool defer = (adt == DT_BF16);
   float* ybuf = nullptr;
-  if (defer_ok) { ybuf = (float*)ws_alloc((size_t)B * Tm * C * 4); if (!ybuf) return AT_ENOMEM; }
+  if (defer) { ybuf = (float*)ws_alloc((size_t)B * Tm * C * 4); if (!ybuf) return AT_ENOMEM; }
 
   // AdaLN parameters of every block + head for all 181 tokens, once per chunk (audio-only)
   GemmArgs g = gemm_args();
@@ -922,7 +921,6 @@ int Engine::ar_chunk_body(int B, const char* scond, const float* style, uint32_t
   for (int p = 0; p < c.n_levels; ++p) {
     const int n_new = c.patch_nums[p], off = p ? tb.cum[p - 1] : 0, M = B * n_new;
     const int sk = n_new <= g_skinny_tokens ? 1 : 0;           // per-clip criterion: batch-size independent arithmetic
-    const bool defer = defer_ok && n_new <= g_ar_defer_max;   // (deferred and fused gated-residual updates are bit-identical)
     const RowMap ada_map = batched_rows(n_new, (int64_t)L * n_ada, n_ada);
     const char* ada_p = ada + (size_t)off * n_ada * s;
     const uint32_t* src_words = forced_words ? forced_words : words;

@@ -130,6 +130,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t st);
 bool attention_tc_supported(const AttnArgs& a);
 void set_attn_simt_max_lq(int v);
 void set_attn_poly(int v);
+void set_attn_blk(int v);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 // AR q/k/v post-processing (app/transformer.py:71-74): per-head L2 normalise q (x exp(min(scale_mul, ln100))) and k,
 // q -> qbuf [M, C]; k,v -> cache rows given by kv_map. qkv: [M, 3C] (q | k | v), or [M, 2C] (k | v) when has_q = 0.

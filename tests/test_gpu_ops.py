@@ -503,6 +503,38 @@ def test_attention_bounded_scores_single_pass(n_seq, H, lq, lk):
     assert (outs[0] - outs[1]).abs().max().item() < 4e-2        # the two evaluations differ by bf16 ulps of P and of the output (|v| <= 4)
 
 
+@pytest.mark.parametrize("n_seq,H,lq,lk", [(2, 12, 100, 362), (3, 12, 50, 262), (70, 12, 100, 362), (64, 12, 50, 262), (40, 12, 150, 384),
+                                           (1, 1, 7, 257)])
+def test_attention_block_wise_kernel(n_seq, H, lq, lk):
+    """attn_blk_kernel: 257..384 keys in two key blocks, one item per warpgroup (two item chains per SM); heads with a usable
+    bound take it as the softmax shift, the head at the clamp (100) runs an online softmax (O rescaled in TMEM). Same result as
+    the split-key kernel within bf16 rounding, and within tolerance of the fp32 reference; from a single item to five items per
+    CTA (stage / barrier phases wrap), ragged last block (262 = 144 + 118 keys), two query tiles (150 rows)."""
+    D = 64
+    g = torch.Generator(device="cpu").manual_seed(lq * 7 + lk + n_seq)
+    Cw = H * D
+    hs = torch.linspace(1.0, 30.0, H)
+    hs[H - 1] = 100.0                                      # the clamp value: this head runs the two blocks as an online softmax
+    q = F.normalize(torch.randn(n_seq, lq, H, D, generator=g), dim=-1) * hs.view(1, 1, H, 1)
+    k = F.normalize(torch.randn(n_seq, lk, H, D, generator=g), dim=-1)
+    q = q.reshape(n_seq, lq, Cw).to(dev(), torch.bfloat16)
+    k = k.reshape(n_seq, lk, Cw).to(dev(), torch.bfloat16)
+    v = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), torch.bfloat16)
+    strides = (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw)
+    bound = hs.to(dev())
+    outs = []
+    try:
+        for blk in (0, 1):
+            _lib.check(_lib.lib().artalk_set_option(b"attn_blk", blk))
+            out = torch.full((n_seq, lq, Cw), float("nan"), device=dev(), dtype=torch.bfloat16)
+            run_attn(q, k, v, out, n_seq, H, D, lq, lk, strides, 1.0, 0, key_bound=bound)
+            _check_attn(out, q, k, v, n_seq, H, D, lq, lk, 1.0, 0, 2e-2)
+            outs.append(out.float())
+    finally:
+        _lib.check(_lib.lib().artalk_set_option(b"attn_blk", 1))
+    assert (outs[0] - outs[1]).abs().max().item() < 4e-2
+
+
 def _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol):
     Cw = H * D
     qq = q.float().view(n_seq, lq, H, D).transpose(1, 2)
