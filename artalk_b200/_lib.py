@@ -159,6 +159,8 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"conv0_fold", int(os.environ["ARTALK_CONV0_FOLD"]))
         if os.environ.get("ARTALK_POSCONV4"):              # 0: positional conv as the N = 64 tap-mode GEMM (A/B switch)
             l.artalk_set_option(b"posconv4", int(os.environ["ARTALK_POSCONV4"]))
+        if os.environ.get("ARTALK_ATTN_BLK"):              # 0: 257..384-key launches take the split-key mode of attn_tc_kernel (A/B switch)
+            l.artalk_set_option(b"attn_blk", int(os.environ["ARTALK_ATTN_BLK"]))
         if os.environ.get("ARTALK_ATTN_POLY"):
             l.artalk_set_option(b"attn_poly", int(os.environ["ARTALK_ATTN_POLY"]))
         if os.environ.get("ARTALK_SKINNY_TOKENS"):
