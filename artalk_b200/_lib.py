@@ -112,6 +112,7 @@ SYMBOLS = {
     "artalk_op_gemm": (C.c_int, [C.POINTER(Gemm), C.c_int, C.c_void_p]),
     "artalk_op_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "artalk_op_attention": (C.c_int, [C.POINTER(Attn), C.c_void_p]),
+    "artalk_op_attention_split": (C.c_int, [C.POINTER(Attn), C.c_void_p, C.c_size_t, C.c_void_p]),
     "artalk_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_float, C.c_int, C.c_void_p]),
     "artalk_op_conv0": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_float, C.c_void_p]),

@@ -33,6 +33,7 @@ int artalk_destroy(artalk_engine_t* e) {
   e->eng.drop_graphs();
   e->eng.free_split();
   if (e->eng.split_buf) cudaFree(e->eng.split_buf);
+  if (e->eng.asplit_buf) cudaFree(e->eng.asplit_buf);
   if (e->eng.ws) cudaFree(e->eng.ws);
   if (e->eng.gstream) cudaStreamDestroy(e->eng.gstream);
   if (e->eng.gev_in) cudaEventDestroy(e->eng.gev_in);
@@ -194,6 +195,7 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "attn_bound")) { g_attn_bound = value; return AT_OK; }
   if (!std::strcmp(name, "posconv4")) { g_posconv4 = value; return AT_OK; }
   if (!std::strcmp(name, "conv0_fold")) { g_conv0_fold = value; return AT_OK; }
+  if (!std::strcmp(name, "attn_split")) { g_attn_split = value; return AT_OK; }
   if (!std::strcmp(name, "attn_poly")) { set_attn_poly(value); return AT_OK; }
   if (!std::strcmp(name, "attn_blk")) { set_attn_blk(value); return AT_OK; }
   if (!std::strcmp(name, "w2v_graph_chunks")) { g_w2v_graph_chunks = value; return AT_OK; }
@@ -238,6 +240,19 @@ int artalk_op_attention(const artalk_attn_t* a, void* stream) {
   x.v_ss = a->v_ss; x.v_rs = a->v_rs; x.o_ss = a->o_ss; x.o_rs = a->o_rs; x.scale = a->scale; x.split = a->split;
   x.key_bound = a->key_bound;
   return launch_attention(x, (cudaStream_t)stream);
+}
+
+int artalk_op_attention_split(const artalk_attn_t* a, void* scratch, size_t scratch_bytes, void* stream) {
+  AT_REQUIRE(a && scratch, "null argument");
+  AttnArgs x;
+  x.q = a->q; x.k = a->k; x.v = a->v; x.out = a->out; x.dt = a->dt; x.n_seq = a->n_seq; x.n_heads = a->n_heads;
+  x.head_dim = a->head_dim; x.lq = a->lq; x.lk = a->lk; x.q_ss = a->q_ss; x.q_rs = a->q_rs; x.k_ss = a->k_ss; x.k_rs = a->k_rs;
+  x.v_ss = a->v_ss; x.v_rs = a->v_rs; x.o_ss = a->o_ss; x.o_rs = a->o_rs; x.scale = a->scale; x.split = a->split;
+  x.key_bound = a->key_bound;
+  AT_REQUIRE(attention_split_supported(x), "attention_split: unsupported shape (lq=%d lk=%d head_dim=%d)", x.lq, x.lk, x.head_dim);
+  AT_REQUIRE(scratch_bytes >= attention_split_scratch_bytes(x), "attention_split: scratch too small (%zu < %zu bytes)", scratch_bytes,
+             attention_split_scratch_bytes(x));
+  return launch_attention_split(x, scratch, (cudaStream_t)stream);
 }
 
 int artalk_op_posconv4(const void* x, const void* w4, const float* bias, const float* resid, float* out, int n_chunks, int frames,

@@ -155,6 +155,35 @@ int launch_simt_rows(const AttnArgs& a, cudaStream_t st) {
 }
 }  // namespace
 
+bool attention_split_supported(const AttnArgs& a) {
+  return a.dt == DT_F32 && attention_tc_split_supported(a.lq, a.lk, a.head_dim) && a.q_rs % 4 == 0 && a.k_rs % 4 == 0 && a.v_rs % 4 == 0 &&
+         a.q_ss % 4 == 0 && a.k_ss % 4 == 0 && a.v_ss % 4 == 0 && a.o_rs % 4 == 0 && a.o_ss % 4 == 0 && ((uintptr_t)a.q % 16 == 0) &&
+         ((uintptr_t)a.k % 16 == 0) && ((uintptr_t)a.v % 16 == 0) && ((uintptr_t)a.out % 16 == 0);
+}
+static size_t pad128(size_t n) { return (n + 127) & ~(size_t)127; }
+size_t attention_split_scratch_bytes(const AttnArgs& a) {
+  const size_t W = (size_t)a.n_heads * a.head_dim;
+  const size_t nq = (size_t)a.n_seq * a.lq * W, nk = (size_t)a.n_seq * a.lk * W;
+  return (pad128(2 * nq) + 2 * pad128(2 * nk)) * sizeof(bf16);
+}
+int launch_attention_split(const AttnArgs& a, void* scratch, cudaStream_t st) {
+  if (a.n_seq <= 0 || a.lq <= 0) return AT_OK;
+  AT_REQUIRE(attention_split_supported(a) && scratch && ((uintptr_t)scratch % 256 == 0), "attention_split: unsupported launch (lq=%d lk=%d)", a.lq, a.lk);
+  const int W = a.n_heads * a.head_dim;
+  const size_t nq = (size_t)a.n_seq * a.lq * W, nk = (size_t)a.n_seq * a.lk * W;
+  bf16* qs = (bf16*)scratch;
+  bf16* ks = qs + pad128(2 * nq);
+  bf16* vs = ks + pad128(2 * nk);
+  // with a single sequence the views may carry a zero sequence stride
+  AT_TRY(launch_split2_rows((const float*)a.q, a.q_ss, a.q_rs, a.n_seq, a.lq, W, qs, st));
+  AT_TRY(launch_split2_rows((const float*)a.k, a.k_ss, a.k_rs, a.n_seq, a.lk, W, ks, st));
+  AT_TRY(launch_split2_rows((const float*)a.v, a.v_ss, a.v_rs, a.n_seq, a.lk, W, vs, st));
+  AttnArgs b = a;
+  b.dt = DT_BF16; b.q = qs; b.k = ks; b.v = vs; b.split_planes = 1;
+  b.q_ss = (int64_t)a.lq * W; b.q_rs = W; b.k_ss = b.v_ss = (int64_t)a.lk * W; b.k_rs = b.v_rs = W;
+  return launch_attention_tc(b, st);
+}
+
 int g_attn_simt_max_lq = 0;     // bf16 launches with at most this many query rows take the SIMT kernel (option "attn_simt_max_lq")
 void set_attn_simt_max_lq(int v) { g_attn_simt_max_lq = v; }
 

@@ -45,7 +45,8 @@ struct AttnTcParams {
   int n_stages, stage_bytes, kv_bytes;
   float scale_log2e;
   const float* bound;        // per-head bound of the scaled scores (null: row maxima from a first pass over S)
-  bf16* out; int64_t o_ss, o_rs;
+  int lo_z;                  // SPLIT kernels: the lo planes of Q / K / V are the sequences [lo_z, 2 lo_z) of the same tensor maps
+  bf16* out; float* out32; int64_t o_ss, o_rs;
   unsigned int* err_flag;
 };
 
@@ -100,7 +101,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 }
 
 // POLY: 0 = every exponential on the MUFU unit, 1 = one in four on the FMA pipe (ex2_poly), 2 = one in two
-template <int POLY>
+// SPLIT (parity-grade mode "bf16x3", fp32 data flow): Q, K, V arrive as two bf16 pieces each (x = hi + lo, planes of one tensor)
+// and both contractions keep the three piece products hi.hi + lo.hi + hi.lo (relative error ~2^-16 per product, as the split
+// GEMMs): S = Qh Kh^T + Ql Kh^T + Qh Kl^T in one accumulator; P is split in registers and written IN PLACE over the 16 S columns
+// just read (hi pieces in the first 8 columns, lo pieces in the last 8), so the three MMA-2 products take their A operands from
+// TMEM without extra columns; O = Ph Vh + Pl Vh + Ph Vl lives outside the S range (columns 192..255 of buffer 0) and leaves as
+// fp32. One stage of operands fills shared memory, so SPLIT launches always run in split-key mode (one item per CTA at a time).
+template <int POLY, bool SPLIT = false>
 __global__ void __launch_bounds__(384, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
@@ -122,6 +129,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   volatile float* xch = reinterpret_cast<volatile float*>(smem_raw + xch_off);       // [kind][parity][wg][128]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SK = p.split_keys;
+  constexpr int OC = SPLIT ? 192 : O_COL;           // O accumulator inside buffer 0 / the item's buffer
+  // operand tiles inside a stage: Q [| Q lo] | K [| K lo] | V [| V lo]
+  const uint32_t QB = SPLIT ? 2u * Q_BYTES : (uint32_t)Q_BYTES, KB = (SPLIT ? 2u : 1u) * (uint32_t)p.kv_bytes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
@@ -152,14 +162,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int st = it % NS;
         const int qt = item % p.q_tiles, sh = item / p.q_tiles, h = sh % p.n_heads, seq = sh / p.n_heads;
         mbar_wait(kv_empty(st), (((uint32_t)(it / NS)) & 1u) ^ 1u, p.err_flag, 0xA77E0001u);
-        const uint32_t sq = smem_base + st * p.stage_bytes, sk = sq + Q_BYTES, sv = sk + p.kv_bytes;
-        mbar_arrive_expect_tx(kv_full(st), (uint32_t)(Q_BYTES + 2 * p.lk_pad * 128));
-        tma_load_3d(sq, &tmQ, kv_full(st), h * 64, qt * QT, seq);
-        tma_load_3d(sk, &tmK, kv_full(st), h * 64, 0, seq);
-        tma_load_3d(sv, &tmV, kv_full(st), h * 64, 0, seq);
-        if (SK) {
-          tma_load_3d(sk + p.h0 * 128, &tmK2, kv_full(st), h * 64, p.h0, seq);
-          tma_load_3d(sv + p.h0 * 128, &tmV2, kv_full(st), h * 64, p.h0, seq);
+        const uint32_t sq = smem_base + st * p.stage_bytes, sk = sq + QB, sv = sk + KB;
+        mbar_arrive_expect_tx(kv_full(st), (SPLIT ? 2u : 1u) * (uint32_t)(Q_BYTES + 2 * p.lk_pad * 128));
+#pragma unroll
+        for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {                   // piece planes: hi, lo
+          const int z = seq + pl * p.lo_z;
+          tma_load_3d(sq + pl * Q_BYTES, &tmQ, kv_full(st), h * 64, qt * QT, z);
+          tma_load_3d(sk + pl * p.kv_bytes, &tmK, kv_full(st), h * 64, 0, z);
+          tma_load_3d(sv + pl * p.kv_bytes, &tmV, kv_full(st), h * 64, 0, z);
+          if (SK) {
+            tma_load_3d(sk + pl * p.kv_bytes + p.h0 * 128, &tmK2, kv_full(st), h * 64, p.h0, z);
+            tma_load_3d(sv + pl * p.kv_bytes + p.h0 * 128, &tmV2, kv_full(st), h * 64, p.h0, z);
+          }
         }
       }
     }
@@ -170,19 +184,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       auto stage_addr = [&](int it) { return smem_base + (uint32_t)((it % NS) * p.stage_bytes); };
       // S = Q K^T for the keys [k0, k0 + n) of item `it` into buffer b
       auto qk = [&](int it, int b, int k0, int n) {
-        const uint32_t sq = stage_addr(it), sk = sq + Q_BYTES + (uint32_t)(k0 * 128);
+        const uint32_t sq = stage_addr(it), sk = sq + QB + (uint32_t)(k0 * 128);
         const uint64_t dq = desc_kmajor_sw128(sq), dk = desc_kmajor_sw128(sk);
         const uint32_t id = idesc(n, 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_ss(tmem + (uint32_t)(b * BUF_COLS), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id, k ? 1u : 0u);
+        if (SPLIT) {                                                     // + Q_lo K_hi^T + Q_hi K_lo^T
+          const uint64_t dql = desc_kmajor_sw128(sq + Q_BYTES), dkl = desc_kmajor_sw128(sk + (uint32_t)p.kv_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(tmem + (uint32_t)(b * BUF_COLS), dql + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(tmem + (uint32_t)(b * BUF_COLS), dq + (uint64_t)(2 * k), dkl + (uint64_t)(2 * k), id, 1u);
+        }
       };
       // O(buffer bo) (+)= P(buffer bp)[keys k0 .. k0+n) V
       auto pv = [&](int it, int bo, int bp, int k0, int n, bool first) {
-        const uint32_t sv = stage_addr(it) + Q_BYTES + (uint32_t)p.kv_bytes;
+        const uint32_t sv = stage_addr(it) + QB + KB;
         const uint64_t dv = desc_mnmajor(sv);
-        for (int ks = 0; ks < (n >> 4); ++ks)
-          mma_ts(tmem + (uint32_t)(bo * BUF_COLS + O_COL), tmem + (uint32_t)(bp * BUF_COLS + ks * 8),
-                 dv + (uint64_t)(((k0 >> 4) + ks) * 128), idesc_pv, (first && ks == 0) ? 0u : 1u);
+        if (!SPLIT) {
+          for (int ks = 0; ks < (n >> 4); ++ks)
+            mma_ts(tmem + (uint32_t)(bo * BUF_COLS + OC), tmem + (uint32_t)(bp * BUF_COLS + ks * 8),
+                   dv + (uint64_t)(((k0 >> 4) + ks) * 128), idesc_pv, (first && ks == 0) ? 0u : 1u);
+        } else {
+          // P of 16 keys sits in the 16 S columns they came from: hi pieces in columns [16 ks, +8), lo pieces in [16 ks + 8, +8)
+          const uint64_t dvl = desc_mnmajor(sv + (uint32_t)p.kv_bytes);
+          for (int ks = 0; ks < (n >> 4); ++ks) {
+            const uint32_t d = tmem + (uint32_t)(bo * BUF_COLS + OC), ah = tmem + (uint32_t)(bp * BUF_COLS + ks * 16);
+            const uint64_t off = (uint64_t)(((k0 >> 4) + ks) * 128);
+            mma_ts(d, ah, dv + off, idesc_pv, (first && ks == 0) ? 0u : 1u);
+            mma_ts(d, ah + 8u, dv + off, idesc_pv, 1u);
+            mma_ts(d, ah, dvl + off, idesc_pv, 1u);
+          }
+        }
       };
       if (!SK) {
         auto mma1 = [&](int it) {
@@ -291,7 +324,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       {
         uint32_t sa[16], sb[16];
         auto emit = [&](const uint32_t (&s0)[16], int c) {
-          uint32_t pk[8];
+          uint32_t pk[8], pl[8];
           const int base = c * 16;
           if (base + 16 <= lk_r) {
 #pragma unroll
@@ -302,6 +335,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               sum2[(j >> 1) & 1] += p0 + p1;
               __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
               pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+              if (SPLIT) {
+                __nv_bfloat162 ll = __floats2bfloat162_rn(p0 - __low2float(hh), p1 - __high2float(hh));
+                pl[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
+              }
             }
           } else {
 #pragma unroll
@@ -311,9 +348,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               sum2[(j >> 1) & 1] += p0 + p1;
               __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
               pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+              if (SPLIT) {
+                __nv_bfloat162 ll = __floats2bfloat162_rn(p0 - __low2float(hh), p1 - __high2float(hh));
+                pl[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
+              }
             }
           }
-          tmem_st8(tb + (uint32_t)(c * 8), pk);
+          if (SPLIT) { tmem_st8(tb + (uint32_t)(c * 16), pk); tmem_st8(tb + (uint32_t)(c * 16 + 8), pl); }
+          else tmem_st8(tb + (uint32_t)(c * 8), pk);
         };
         if (n16 > 0) tmem_ld16_nowait(tb, sa);
         for (int c = 0; c < n16; c += 2) {
@@ -327,7 +369,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        for (int c = n16; c < n16_all; ++c) tmem_st8(tb + (uint32_t)(c * 8), zero);      // masked for every row of the warp
+        for (int c = n16; c < n16_all; ++c) {                                                 // masked for every row of the warp
+          if (SPLIT) { tmem_st8(tb + (uint32_t)(c * 16), zero); tmem_st8(tb + (uint32_t)(c * 16 + 8), zero); }
+          else tmem_st8(tb + (uint32_t)(c * 8), zero);
+        }
       }
       float sum = sum2[0] + sum2[1];
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -344,7 +389,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float inv = 1.0f / sum;
       // ---- epilogue: ping-pong -> all 64 columns of the own buffer; split keys -> 32 columns of buffer 0's O
       const int c_first = SK ? wg * 32 : 0;
-      const uint32_t ob = tmem + lane_addr + (uint32_t)((SK ? 0 : b) * BUF_COLS + O_COL + c_first);
+      const uint32_t ob = tmem + lane_addr + (uint32_t)((SK ? 0 : b) * BUF_COLS + OC + c_first);
       uint32_t o0[16], o1[16], o2[16], o3[16];
       if (warp_live) {
         tmem_ld16_nowait(ob, o0);
@@ -355,7 +400,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(bar));                    // S/P/O of this buffer may be overwritten
-      if (warp_live && qi < p.lq) {
+      if (SPLIT && warp_live && qi < p.lq) {
+        float* orow = p.out32 + (int64_t)seq * p.o_ss + (int64_t)qi * p.o_rs + h * 64 + c_first;
+        auto store16f = [&](const uint32_t (&o)[16], int col) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(orow + col + j) = make_float4(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv,
+                                                                     __uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+        };
+        store16f(o0, 0);
+        store16f(o1, 16);
+        if (!SK) { store16f(o2, 32); store16f(o3, 48); }
+      } else if (warp_live && qi < p.lq) {
         bf16* orow = p.out + (int64_t)seq * p.o_ss + (int64_t)qi * p.o_rs + h * 64 + c_first;
         auto store16 = [&](const uint32_t (&o)[16], int col) {
 #pragma unroll
@@ -677,6 +733,14 @@ void set_attn_blk(int v) { g_attn_blk = v; }
 int g_attn_poly = 0;       // option "attn_poly": share of the softmax exponentials computed on the FMA pipe (0, 1 = 1/4, 2 = 1/2)
 void set_attn_poly(int v) { g_attn_poly = v < 0 ? 0 : (v > 2 ? 2 : v); }
 
+// parity-grade launches (AttnArgs::split_planes): two key halves of 16..192 keys, one stage of hi + lo tiles in shared memory
+bool attention_tc_split_supported(int lq, int lk, int head_dim) {
+  const int lk_pad = (lk + 15) & ~15;
+  const int h0 = ((lk_pad / 2) + 15) & ~15;
+  return head_dim == 64 && lq >= 1 && lk_pad >= 32 && lk_pad - h0 >= 16 && h0 <= 192 &&
+         2 * Q_BYTES + 4 * lk_pad * 128 + 1024 + 256 + XCH_BYTES <= SMEM_LIMIT;
+}
+
 bool attention_tc_supported(const AttnArgs& a) {
   return a.dt == DT_BF16 && a.head_dim == 64 && a.lk <= MAX_LK && a.lk >= 1 && a.q_rs % 8 == 0 && a.k_rs % 8 == 0 &&
          a.v_rs % 8 == 0 && a.q_ss % 8 == 0 && a.k_ss % 8 == 0 && a.v_ss % 8 == 0 && a.o_rs % 8 == 0 && a.o_ss % 8 == 0 &&
@@ -693,13 +757,17 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<0>, SMEM_LIMIT));
   AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<1>, SMEM_LIMIT));
   AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<2>, SMEM_LIMIT));
+  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<0, true>, SMEM_LIMIT));
+  const bool split = a.split_planes != 0;
+  AT_REQUIRE(!split || (attention_tc_split_supported(a.lq, a.lk, a.head_dim) && a.q_ss > 0 && a.k_ss > 0 && a.v_ss > 0 && a.o_rs % 4 == 0 &&
+                        a.o_ss % 4 == 0), "attention_tc: unsupported split launch (lq=%d lk=%d)", a.lq, a.lk);
   AttnTcParams p;
   p.n_heads = a.n_heads; p.lq = a.lq; p.lk = a.lk;
   p.lk_pad = (a.lk + 15) & ~15;
-  p.split_keys = p.lk_pad > BUF_COLS ? 1 : 0;
+  p.split_keys = (split || p.lk_pad > BUF_COLS) ? 1 : 0;
   p.h0 = p.split_keys ? (((p.lk_pad / 2) + 15) & ~15) : p.lk_pad;
   p.kv_bytes = p.lk_pad * 128;                      // lk_pad is a multiple of 16 rows -> a multiple of 2048 B (1024 B swizzle atoms)
-  p.stage_bytes = Q_BYTES + 2 * p.kv_bytes;
+  p.stage_bytes = split ? 2 * Q_BYTES + 4 * p.kv_bytes : Q_BYTES + 2 * p.kv_bytes;
   p.q_tiles = ceil_div(a.lq, QT);
   p.total_items = a.n_seq * a.n_heads * p.q_tiles;
   const int fixed = 1024 /*align*/ + 256 /*barriers*/ + XCH_BYTES;
@@ -709,23 +777,30 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   p.split = a.split;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.bound = a.key_bound;
-  p.out = (bf16*)a.out; p.o_ss = a.o_ss; p.o_rs = a.o_rs;
+  p.out = (bf16*)a.out; p.out32 = (float*)a.out; p.o_ss = a.o_ss; p.o_rs = a.o_rs;
+  p.lo_z = split ? a.n_seq : 0;
+  const uint64_t n_z = (uint64_t)a.n_seq * (split ? 2 : 1);          // the lo planes are the sequences [n_seq, 2 n_seq) of each tensor
   p.err_flag = g_err_flag;
   CUtensorMap tmQ, tmK, tmV, tmK2, tmV2;
   const uint64_t wq = (uint64_t)a.n_heads * 64;
   auto ss = [](int64_t s, int64_t rs, int rows) { return (uint64_t)(s > 0 ? s : rs * rows) * 2; };   // n_seq == 1: any stride
-  AT_TRY(make_map(&tmQ, a.q, wq, (uint64_t)a.lq, (uint64_t)a.n_seq, (uint64_t)a.q_rs * 2, ss(a.q_ss, a.q_rs, a.lq), QT));
-  AT_TRY(make_map(&tmK, a.k, wq, (uint64_t)a.lk, (uint64_t)a.n_seq, (uint64_t)a.k_rs * 2, ss(a.k_ss, a.k_rs, a.lk), (uint32_t)p.h0));
-  AT_TRY(make_map(&tmV, a.v, wq, (uint64_t)a.lk, (uint64_t)a.n_seq, (uint64_t)a.v_rs * 2, ss(a.v_ss, a.v_rs, a.lk), (uint32_t)p.h0));
+  AT_TRY(make_map(&tmQ, a.q, wq, (uint64_t)a.lq, n_z, (uint64_t)a.q_rs * 2, ss(a.q_ss, a.q_rs, a.lq), QT));
+  AT_TRY(make_map(&tmK, a.k, wq, (uint64_t)a.lk, n_z, (uint64_t)a.k_rs * 2, ss(a.k_ss, a.k_rs, a.lk), (uint32_t)p.h0));
+  AT_TRY(make_map(&tmV, a.v, wq, (uint64_t)a.lk, n_z, (uint64_t)a.v_rs * 2, ss(a.v_ss, a.v_rs, a.lk), (uint32_t)p.h0));
   tmK2 = tmK; tmV2 = tmV;
   if (p.split_keys) {
     const uint32_t r2 = (uint32_t)(p.lk_pad - p.h0);
-    AT_TRY(make_map(&tmK2, a.k, wq, (uint64_t)a.lk, (uint64_t)a.n_seq, (uint64_t)a.k_rs * 2, ss(a.k_ss, a.k_rs, a.lk), r2));
-    AT_TRY(make_map(&tmV2, a.v, wq, (uint64_t)a.lk, (uint64_t)a.n_seq, (uint64_t)a.v_rs * 2, ss(a.v_ss, a.v_rs, a.lk), r2));
+    AT_TRY(make_map(&tmK2, a.k, wq, (uint64_t)a.lk, n_z, (uint64_t)a.k_rs * 2, ss(a.k_ss, a.k_rs, a.lk), r2));
+    AT_TRY(make_map(&tmV2, a.v, wq, (uint64_t)a.lk, n_z, (uint64_t)a.v_rs * 2, ss(a.v_ss, a.v_rs, a.lk), r2));
   }
   const size_t smem = (size_t)p.n_stages * p.stage_bytes + fixed;
   const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
   g_trace_dims[0] = a.n_seq * a.n_heads; g_trace_dims[1] = a.lq; g_trace_dims[2] = a.lk;
+  if (split) {
+    AT_CUDA(launch_k(attn_tc_kernel<0, true>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
+    AT_LAUNCH_CHECK();
+    return AT_OK;
+  }
   if (g_attn_blk && p.split_keys && a.key_bound && a.split == 0) {
     // two key blocks per item, one item per warpgroup (see attn_blk_kernel); heads without a usable bound run online
     AT_TRY(ensure_dyn_smem((const void*)attn_blk_kernel, SMEM_BLK));

@@ -183,6 +183,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 extern bool g_pdl;        // host switch (artalk_enable_pdl); default on
 extern int g_pdl_w2v_max_chunks;   // wav2vec sub-batches larger than this run without PDL (option "pdl_w2v_max_chunks")
 extern int g_skinny_tokens;   // option "skinny_tokens" (engine.cu)
+extern int g_attn_split;      // option "attn_split" (engine.cu)
 extern int g_conv0_fold;      // option "conv0_fold" (engine.cu)
 extern int g_posconv4;        // option "posconv4" (engine.cu)
 extern int g_attn_bound;      // option "attn_bound" (engine.cu)

@@ -199,6 +199,35 @@ void Engine::free_split() {
   wsplit.clear();
 }
 
+// Piece buffers of the parity-grade modes grow on demand (outside graph capture: the eager warm-up call of a chunk sizes them)
+int Engine::grow_piece_buffer(char*& buf, size_t& cap, size_t bytes, cudaStream_t st) {
+  if (bytes <= cap) return AT_OK;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  AT_CUDA(cudaStreamIsCapturing(st, &cs));
+  AT_REQUIRE(cs == cudaStreamCaptureStatusNone, "piece buffer would have to grow during graph capture");
+  AT_CUDA(cudaStreamSynchronize(st));
+  if (gstream) AT_CUDA(cudaStreamSynchronize(gstream));
+  drop_graphs();                          // captured launches point into the old buffer
+  if (buf) { AT_CUDA(cudaFree(buf)); buf = nullptr; cap = 0; }
+  const size_t want = bytes + bytes / 4 + (1 << 20);
+  cudaError_t e = cudaMalloc((void**)&buf, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("piece buffer: cudaMalloc(%zu MiB) failed: %s", want >> 20, cudaGetErrorString(e));
+    return AT_ENOMEM;
+  }
+  cap = want;
+  return AT_OK;
+}
+
+// Attention at fp32 grade on the tensor cores (precision "bf16x3"): q, k, v (fp32, strided views) are split into two bf16 piece
+// planes each and the SPLIT variant of the tcgen05 kernel keeps the three piece products of both contractions
+// (attention_tc.cu). Shapes it cannot take (head_dim 32, fewer than 17 or more than 368 keys) stay on the fp32 SIMT kernel.
+int Engine::attention_split(const AttnArgs& a, cudaStream_t st) {
+  AT_TRY(grow_piece_buffer(asplit_buf, asplit_cap, attention_split_scratch_bytes(a), st));
+  return launch_attention_split(a, asplit_buf, st);
+}
+
 // C = A W^T on the tensor cores at fp32 grade: A is split into bf16 piece blocks on the fly, W was split by finalize, and the
 // bf16 GEMM kernel runs the `slots` piece products as one GEMM with K' = slots * K (split.cu). Shapes the block layout cannot
 // express (K or a stride not a multiple of 64: the VAE decoder's 32-wide input mapping) take the fp32 CUDA-core kernel.
@@ -218,23 +247,7 @@ int Engine::gemm_split(const GemmArgs& g, cudaStream_t st) {
     extent = (int64_t)(g.M - 1) * g.a_map.rs + g.K;
   }
   const size_t bytes = (size_t)extent * S * sizeof(bf16);
-  if (bytes > split_cap) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    AT_CUDA(cudaStreamIsCapturing(st, &cs));
-    AT_REQUIRE(cs == cudaStreamCaptureStatusNone, "gemm_split: operand buffer would have to grow during graph capture");
-    AT_CUDA(cudaStreamSynchronize(st));
-    if (gstream) AT_CUDA(cudaStreamSynchronize(gstream));
-    drop_graphs();                          // captured launches point into the old buffer
-    if (split_buf) { AT_CUDA(cudaFree(split_buf)); split_buf = nullptr; split_cap = 0; }
-    const size_t want = bytes + bytes / 4 + (1 << 20);
-    cudaError_t e = cudaMalloc((void**)&split_buf, want);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_last_error("gemm_split: cudaMalloc(%zu MiB) failed: %s", want >> 20, cudaGetErrorString(e));
-      return AT_ENOMEM;
-    }
-    split_cap = want;
-  }
+  AT_TRY(grow_piece_buffer(split_buf, split_cap, bytes, st));
   AT_TRY(launch_split_bf16((const float*)g.A, split_buf, extent, S, 0, st));
   GemmArgs h = g;
   h.A = split_buf; h.a_map.rs *= S; h.a_map.bs *= S;
@@ -318,6 +331,7 @@ int g_skinny_tokens = 1;        // AR scale steps with at most this many new tok
 int g_pdl_mask = 3;            // measured in the chunk graph: GEMM/attention edges help (-3.4 %), elementwise edges cancel it
 int g_pdl_w2v_max_chunks = 1 << 30;
 int g_w2v_graph_chunks = 4;     // option "w2v_graph_chunks": wav2vec calls with at most this many chunks replay a CUDA graph
+int g_attn_split = 1;          // option "attn_split": precision bf16x3 runs attention on the tensor cores from two bf16 pieces per operand
 int g_conv0_fold = 1;          // option "conv0_fold": bf16 mode runs conv layer 0 with the LayerNorm folded through the conv (conv0_fold.cu)
 int g_posconv4 = 1;            // option "posconv4": bf16 mode runs the positional conv in its four-frames-per-row form (posconv_tc.cu)
 int g_attn_bound = 1;          // option "attn_bound": AR attention subtracts the per-head score bound instead of the row maximum
@@ -424,7 +438,9 @@ int Engine::gemm(const GemmArgs& g0, cudaStream_t st) {
 
 int Engine::attention(const AttnArgs& a, cudaStream_t st) {
   double keys = (a.split > 0) ? 0.5 * (a.split + a.lk) : a.lk;     // rows < split see `split` keys, the rest see lk
-  PROF_WRAP(1, 4.0 * a.n_seq * a.n_heads * a.head_dim * a.lq * keys, a.n_seq * a.n_heads, a.lq, a.lk, launch_attention(a, st));
+  const bool tc_split = cfg.precision == 2 && g_attn_split && attention_split_supported(a);
+  PROF_WRAP(1, 4.0 * a.n_seq * a.n_heads * a.head_dim * a.lq * keys, a.n_seq * a.n_heads, a.lq, a.lk,
+            tc_split ? attention_split(a, st) : launch_attention(a, st));
 }
 
 int Engine::posconv4(const void* x, const void* w4, const float* bias, const float* resid, float* out, int n, cudaStream_t st) {

@@ -44,6 +44,9 @@ struct Engine {
   // device pointer, and a grow-on-demand buffer for the piece blocks of the current GEMM's A operand
   std::map<const void*, void*> wsplit;
   char* split_buf = nullptr; size_t split_cap = 0;
+  char* asplit_buf = nullptr; size_t asplit_cap = 0;      // q / k / v piece planes of the parity-grade attention
+  int grow_piece_buffer(char*& buf, size_t& cap, size_t bytes, cudaStream_t st);
+  int attention_split(const AttnArgs& a, cudaStream_t st);
   int gemm_split(const GemmArgs& g, cudaStream_t st);
   void free_split();
 

@@ -108,6 +108,9 @@ int launch_posconv4(const void* x, const void* w4, const float* bias, const floa
 // fp32 [n_elems] -> bf16 piece blocks [n_elems / 64][slots][64] (slots 3: 2 pieces / 3 MMA passes, 6: 3 pieces / 6 passes);
 // is_w selects the weight-side slot order so that slot s of A times slot s of W enumerates the kept piece products
 int launch_split_bf16(const float* x, void* out, int64_t n_elems, int slots, int is_w, cudaStream_t st);
+// fp32 rows x[seq][row][0 .. cols) (sequence stride ss, row stride rs) -> two bf16 piece planes out[2][n_seq][rows][cols]
+// (hi = bf16(x), lo = bf16(x - hi)): the operands of the parity-grade attention (attention_tc.cu, SPLIT). cols % 8 == 0
+int launch_split2_rows(const float* x, int64_t ss, int64_t rs, int n_seq, int rows, int cols, void* out, cudaStream_t st);
 
 // ---------------- attention.cu ----------------
 struct AttnArgs {
@@ -124,10 +127,19 @@ struct AttnArgs {
   // L2-normalised per head, app/transformer.py:72-74, so |q.k| <= head_scale[h]). The tcgen05 kernel then subtracts the bound
   // instead of the row maximum (softmax is shift invariant) and skips its max pass over S; ignored by the SIMT kernel
   const float* key_bound = nullptr;
+  // parity-grade tensor-core launch (precision "bf16x3"): q / k / v point to the bf16 HI planes of [2][n_seq][rows][width] piece
+  // tensors (x = hi + lo, launch_split2_rows; the lo plane of a tensor starts n_seq * its sequence stride later) and `out` is fp32
+  int split_planes = 0;
 };
 // dispatch: bf16 / head_dim 64 / <= 384 keys -> tcgen05 kernel (attention_tc.cu), otherwise the fp32-arithmetic SIMT kernel
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 bool attention_tc_supported(const AttnArgs& a);
+bool attention_tc_split_supported(int lq, int lk, int head_dim);
+// fp32-grade attention on the tensor cores (precision "bf16x3"): a.q / a.k / a.v / a.out are fp32 views; `scratch`
+// (attention_split_scratch_bytes(a) bytes, 256-byte aligned) receives the two bf16 piece planes of each operand
+bool attention_split_supported(const AttnArgs& a);
+size_t attention_split_scratch_bytes(const AttnArgs& a);
+int launch_attention_split(const AttnArgs& a, void* scratch, cudaStream_t st);
 void set_attn_simt_max_lq(int v);
 void set_attn_poly(int v);
 void set_attn_blk(int v);

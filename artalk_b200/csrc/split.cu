@@ -60,7 +60,44 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
   }
 }
 
+// one thread = 8 consecutive elements of a row; planes are compact [n_seq][rows][cols]
+__global__ void __launch_bounds__(256) split2_rows_kernel(const float* __restrict__ x, int64_t ss, int64_t rs, int rows, int cols8,
+                                                          bf16* __restrict__ out, int64_t plane, int64_t total8) {
+  pdl_enter();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cols8);
+    const int64_t r = i / cols8;
+    const int row = (int)(r % rows);
+    const int64_t seq = r / rows;
+    const float* src = x + seq * ss + (int64_t)row * rs + c8 * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { hi[e] = __bfloat162float(__float2bfloat16_rn(v[e])); lo[e] = v[e] - hi[e]; }
+    uint4 ph, pl;
+    ph.x = pack2(hi[0], hi[1]); ph.y = pack2(hi[2], hi[3]); ph.z = pack2(hi[4], hi[5]); ph.w = pack2(hi[6], hi[7]);
+    pl.x = pack2(lo[0], lo[1]); pl.y = pack2(lo[2], lo[3]); pl.z = pack2(lo[4], lo[5]); pl.w = pack2(lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(out + i * 8) = ph;
+    *reinterpret_cast<uint4*>(out + plane + i * 8) = pl;
+  }
+}
+
 }  // namespace
+
+int launch_split2_rows(const float* x, int64_t ss, int64_t rs, int n_seq, int rows, int cols, void* out, cudaStream_t st) {
+  if (n_seq <= 0 || rows <= 0) return AT_OK;
+  AT_REQUIRE(x && out && cols % 8 == 0 && ss % 4 == 0 && rs % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0),
+             "split2_rows: bad argument (cols=%d)", cols);
+  const int64_t plane = (int64_t)n_seq * rows * cols, total8 = plane / 8;
+  int64_t blocks = (total8 + 255) / 256;
+  const DevCtx* dc = nullptr;
+  AT_TRY(dev_ctx(&dc));
+  if (blocks > (int64_t)dc->num_sms * 16) blocks = (int64_t)dc->num_sms * 16;
+  AT_CUDA(launch_k(split2_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, ss, rs, rows, cols / 8, (bf16*)out, plane, total8));
+  AT_LAUNCH_CHECK();
+  return AT_OK;
+}
 
 // x [n_elems] fp32 (n_elems % 64 == 0, 16-byte aligned) -> out [n_elems / 64][slots][64] bf16; slots = 3 or 6
 int launch_split_bf16(const float* x, void* out, int64_t n_elems, int slots, int is_w, cudaStream_t st) {

@@ -223,6 +223,10 @@ typedef struct artalk_attn {
   const float* key_bound;        /* optional [n_heads] device array: |q.k| * scale <= key_bound[h] (bf16 tensor-core kernel: one pass) */
 } artalk_attn_t;
 int artalk_op_attention(const artalk_attn_t* a, void* stream);
+/* fp32-grade attention on the tensor cores (precision "bf16x3"): q / k / v / out fp32 (dt = ARTALK_F32), head_dim 64, 17..368 keys.
+ * Operands are split into two bf16 pieces each in `scratch` (256-byte aligned device memory,
+ * 4 * n_seq * (lq + 2 * lk) * n_heads * 64 bytes + 1 KiB is enough) and both contractions keep the three piece products. */
+int artalk_op_attention_split(const artalk_attn_t* a, void* scratch, size_t scratch_bytes, void* stream);
 int artalk_op_layernorm(const float* x, void* out, int out_dt, const float* gamma, const float* beta, int rows, int cols,
                         float eps, int act, void* stream);
 /* wav2vec2 feature-extractor layer 0 (modeling_wav2vec2.py:291-299: Conv1d(1, 512, k=10, s=5) + LayerNorm + GELU) on per-chunk
