@@ -686,12 +686,15 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
 // RB (EPI 1): residual-chunk buffers per epilogue half. RB = 2 trades one operand stage for two more 16 KB buffers so that two
 // residual TMA loads per half are in flight: for K <= 2048 (the wav2vec out-projection: 16 k-blocks per tile) the epilogue,
 // not the MMA ring, is the critical path and each chunk exposed most of a DRAM round trip (~3 us per 32-column chunk).
-template <int EPI, int RB = 1>
+// SPLIT2 (parity-grade modes, operands are bf16 piece blocks): 256 x 128 pair tiles whose accumulator stage holds the main (p0 x p0)
+// and the correction accumulator side by side (2 x 128 columns, as gemm_tc_kernel<.., SPLIT>), two stages = the 512 TMEM columns.
+template <int EPI, int RB = 1, bool SPLIT2 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmO, const TcParams p) {
-  constexpr int BN = 256;
+  constexpr int BN = SPLIT2 ? 128 : 256;
+  constexpr int ACC = SPLIT2 ? 2 * BN : BN;                      // TMEM columns per accumulator stage
   constexpr int NST = EPI == 1 ? STAGES2 - RB : STAGES2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -791,15 +794,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u, p.err_flag, 0x22);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC);
+        int slot = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, p.err_flag, 0x23);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A_STAGE_BYTES;
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+          // SPLIT2: slot 0 of a K block -> main accumulator, the others -> correction accumulator (first use of each overwrites)
+          const bool corr = SPLIT2 && slot != 0;
+          const uint32_t d_acc = corr ? d_tmem + (uint32_t)BN : d_tmem;
+          const int first_kb = corr ? 1 : 0;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            tc_mma_bf16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_bf16_2sm(d_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb != first_kb || k != 0) ? 1u : 0u);
+          if (SPLIT2 && ++slot == p.split_slots) slot = 0;
           tc_commit_2sm(empty_bar(stage));         // frees the slot in both CTAs once these MMAs have read it
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
@@ -866,8 +875,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(rfull_bar(ridx), (r_use / RB) & 1u, p.err_flag, 0x26);
           rsm = reinterpret_cast<const float4*>(smem_raw + (rbuf_base - smem_u32(smem_raw)) + ridx * RBUF_BYTES + (q * 32 + lane) * 128);
         }
-        epi_chunk<EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), row_ok, c_off, g_off, r_off, p.bias,
-                       col_base + c * 32, gate_bf, scr, lane, rsm, tmo, mt * 256 + (int)rank * 128 + q * 32, b);
+        epi_chunk<EPI, SPLIT2 ? BN : 0>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC + c * 32), row_ok, c_off, g_off, r_off,
+                                        p.bias, col_base + c * 32, gate_bf, scr, lane, rsm, tmo, mt * 256 + (int)rank * 128 + q * 32, b);
         if (EPI == 1 && p.tma_resid) {             // the row was copied to registers at the top of epi_chunk
           __syncwarp();
           if (lane == 0) mbar_arrive(rempty_bar(ridx));
@@ -976,20 +985,20 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
   return launch_bn_epi<BN, 0>(tmA, tmW, tmWt, tmO, p, st);
 }
 
-template <int EPI, int RB = 1>
+template <int EPI, int RB = 1, bool SPLIT2 = false>
 int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmR,
                     const CUtensorMap& tmO, const TcParams& p, cudaStream_t st) {
   static int max_clusters_dev[16] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
   int& max_clusters = per_device_slot(max_clusters_dev);
   if (max_clusters < 0) {
-    AT_TRY(ensure_dyn_smem((const void*)gemm_tc2_kernel<EPI, RB>, SMEM2_BYTES));
+    AT_TRY(ensure_dyn_smem((const void*)gemm_tc2_kernel<EPI, RB, SPLIT2>, SMEM2_BYTES));
     cudaLaunchConfig_t qc = {};
     qc.gridDim = dim3(g_num_sms & ~1); qc.blockDim = dim3(384); qc.dynamicSmemBytes = SMEM2_BYTES;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.attrs = qa; qc.numAttrs = 1;
     int n = 0;
-    AT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<EPI, RB>, &qc));
+    AT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<EPI, RB, SPLIT2>, &qc));
     max_clusters = n > 0 ? n : 1;
     if (getenv("ARTALK_DEBUG")) fprintf(stderr, "[artalk] gemm pair kernel EPI=%d: max active clusters %d (SMs %d)\n", EPI, n, g_num_sms);
     if (max_clusters > g_num_sms / 2) max_clusters = g_num_sms / 2;
@@ -1002,7 +1011,7 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_on() ? 2 : 1;
-  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI, RB>, tmA, tmW, tmWt, tmR, tmO, p));
+  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI, RB, SPLIT2>, tmA, tmW, tmWt, tmR, tmO, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -1011,6 +1020,7 @@ int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
 int g_tma_out = 2;        // (declared above make_out_map) option "gemm_tma_out": 0 = st.global epilogue, 1 = TMA stores for fp32-only outputs, 2 = also bf16-only outputs
 int g_resid_deep = 1;     // option "gemm_resid_deep": residual buffers per epilogue half beyond one: 1 -> two for K <= 2048, 2 -> also three for K <= 1024
 int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
+int g_pair_split = 1;     // option "gemm_pair_split": parity-grade (piece-block) GEMMs may take the CTA-pair kernel (256 x 128 tiles)
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
 }  // namespace
@@ -1021,6 +1031,7 @@ void set_gemm_tma_resid(int on) { g_tma_resid = on; }
 void set_gemm_band_mb(int mb) { g_band_mb = mb; }
 void set_gemm_tma_out(int on) { g_tma_out = on; }
 void set_gemm_resid_deep(int on) { g_resid_deep = on; }
+void set_gemm_pair_split(int on) { g_pair_split = on; }
 
 int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   GemmArgs g = g_in;
@@ -1048,25 +1059,28 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   AT_REQUIRE(!batched || g.M % g.a_map.rpb == 0, "gemm_tc: M must be a multiple of the A view's rows per batch");
   p.tiles_per_batch = ceil_div(p.rpb, BM);
   // CTA-pair kernel (256x256 tiles over two SMs) for the large plain GEMMs: >= 4 waves of pair tiles at >= 85 % wave efficiency
-  if (g_pair_mode && !g.split_acc && !g.tap_w && g.groups == 1 && !g.qkv_mode && g.N >= 256 && g.N % 128 == 0) {
-    const int tpb2 = ceil_div(p.rpb, 256), n_tiles_n2 = ceil_div(g.N, 256), n_cl = g_num_sms / 2;
+  const bool pair_split = g.split_acc != 0;
+  if (g_pair_mode && (!pair_split || (g_pair_split && (g.K / BK) % g.split_acc == 0)) && !g.tap_w && g.groups == 1 && !g.qkv_mode && g.N >= 256 &&
+      g.N % 128 == 0) {
+    const int BN2 = pair_split ? 128 : 256;                        // piece-block GEMMs: main | correction accumulators of 128 columns
+    const int tpb2 = ceil_div(p.rpb, 256), n_tiles_n2 = ceil_div(g.N, BN2), n_cl = g_num_sms / 2;
     const long tiles2 = (long)p.n_batches * tpb2 * n_tiles_n2;
     const double row_eff = (double)p.rpb / ((double)tpb2 * 256.0);
     // ragged last wave: its tiles are cut into column slices (>= 32 wide) that run side by side on the idle CTA pairs
     const int rem2 = (int)(tiles2 % n_cl);
     int split2 = 1;
-    if (rem2 > 0) while (256 / (split2 * 2) >= 32 && rem2 * split2 * 2 <= n_cl) split2 *= 2;
+    if (rem2 > 0) while (BN2 / (split2 * 2) >= 32 && rem2 * split2 * 2 <= n_cl) split2 *= 2;
     const double waves_eff = (double)(tiles2 / n_cl) + (rem2 ? (split2 > 1 ? 1.3 / split2 : 1.0) : 0.0);
     if (tiles2 >= 4L * n_cl && (double)tiles2 / (waves_eff * n_cl) >= 0.85 && row_eff >= 0.85 && tiles2 < (1L << 30)) {
       p.tiles_per_batch = tpb2; p.n_tiles_n = n_tiles_n2; p.groups = 1;
       if (g_band_mb > 0 && (double)g.N * g.K * 2.0 > 2.0 * g_band_mb * 1048576.0) {
-        const int bn_tiles = (int)((double)g_band_mb * 1048576.0 / (256.0 * g.K * 2.0));
+        const int bn_tiles = (int)((double)g_band_mb * 1048576.0 / ((double)BN2 * g.K * 2.0));
         p.band_n = bn_tiles < 1 ? 1 : bn_tiles;
       }
-      p.main_tiles = (int)tiles2 - (split2 > 1 ? rem2 : 0); p.tail_split = split2; p.tail_bn = 256 / split2;
+      p.main_tiles = (int)tiles2 - (split2 > 1 ? rem2 : 0); p.tail_split = split2; p.tail_bn = BN2 / split2;
       p.total_tiles = p.main_tiles + (split2 > 1 ? rem2 * split2 : 0);
       p.num_kb = ceil_div(g.K, BK);
-      p.tap_mode = 0; p.tap_pad = 0; p.a_group_cols = 0; p.tap_slots = 1; p.exact = g.exact; p.split_slots = 0;
+      p.tap_mode = 0; p.tap_pad = 0; p.a_group_cols = 0; p.tap_slots = 1; p.exact = g.exact; p.split_slots = g.split_acc;
       p.c_gs = 0; p.bias_gs = 0; p.bias = g.bias; p.act = g.act;
       p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
       p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;
@@ -1084,14 +1098,14 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
       const uint64_t a_s1 = (uint64_t)g.a_map.rs * 2;
       const uint64_t a_s2 = batched ? (uint64_t)g.a_map.bs * 2 : (uint64_t)p.rpb * g.a_map.rs * 2;
       AT_TRY(make_map_3d(&tmA2, g.A, (uint64_t)g.K, (uint64_t)p.rpb, (uint64_t)p.n_batches, a_s1, a_s2 ? a_s2 : 16, BK, 128));
-      AT_TRY(make_map_3d(&tmW2, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.ldw * 2, (uint64_t)g.N * g.ldw * 2, BK, 128));
+      AT_TRY(make_map_3d(&tmW2, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.ldw * 2, (uint64_t)g.N * g.ldw * 2, BK, (uint32_t)(BN2 / 2)));
       CUtensorMap tmW2t = tmW2;
       if (p.tail_split > 1)
         AT_TRY(make_map_3d(&tmW2t, g.W, (uint64_t)g.K, (uint64_t)g.N, 1, (uint64_t)g.ldw * 2, (uint64_t)g.N * g.ldw * 2, BK,
                            (uint32_t)(p.tail_bn / 2)));
       // fp32 residual by TMA: plain contiguous-row residual, 16-byte aligned rows, whole 32-column chunks
       CUtensorMap tmR = tmW2;
-      p.tma_resid = (g_tma_resid && g.resid && !g.gate && p.vec_ok && g.resid_map.rpb <= 0 && g.N % 32 == 0 && g.resid_map.rs % 4 == 0 &&
+      p.tma_resid = (g_tma_resid && !pair_split && g.resid && !g.gate && p.vec_ok && g.resid_map.rpb <= 0 && g.N % 32 == 0 && g.resid_map.rs % 4 == 0 &&
                      ((uintptr_t)g.resid % 16 == 0)) ? 1 : 0;
       if (p.tma_resid)
         AT_TRY(make_map_3d(&tmR, g.resid, (uint64_t)g.N, (uint64_t)g.M, 1, (uint64_t)g.resid_map.rs * 4, (uint64_t)g.M * g.resid_map.rs * 4,
@@ -1101,6 +1115,10 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
         const int t = make_out_map(&tmO, g, p.rpb, p.n_batches, p.vec_ok != 0);
         if (t < 0) return AT_ECUDA;
         p.tma_out = t;
+      }
+      if (pair_split) {
+        if (p.gate || p.resid) return launch_pair_epi<1, 1, true>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
+        return launch_pair_epi<0, 1, true>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       }
       if (p.tma_resid && g_resid_deep >= 2 && p.num_kb <= 16) return launch_pair_epi<1, 3>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (p.tma_resid && g_resid_deep >= 1 && p.num_kb <= 32) return launch_pair_epi<1, 2>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);

@@ -1,0 +1,18 @@
+#!/bin/bash
+# GPU session 12 of round 2: CTA-pair kernel for the piece-block (parity-grade) GEMMs
+set -x
+cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "split or gemm" --timeout 120 > gpurun_out/r2m_gemm_test.log 2>&1; rc=$?; echo "gemm rc=$rc"
+tail -12 gpurun_out/r2m_gemm_test.log | cut -c1-300
+if [ $rc -ne 0 ]; then echo "gemm tests failed: stopping"; exit 0; fi
+rm -f gpurun_out/parity_measured.jsonl
+timeout 1200 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/r2m_pytest.log 2>&1; echo "pytest rc=$?"
+tail -8 gpurun_out/r2m_pytest.log | cut -c1-400
+grep -E "bf16x3|bf16x6" gpurun_out/parity_measured.jsonl | cut -c1-330
+timeout 900 python tools_ab.py --precision bf16x3 --clips 64 --seconds 10 --rounds 2 --steps 2 base gemm_pair_split=0 > gpurun_out/r2m_ab_64x10_x3.json 2> gpurun_out/r2m_ab_64x10_x3.err
+cat gpurun_out/r2m_ab_64x10_x3.json; tail -3 gpurun_out/r2m_ab_64x10_x3.err
+timeout 900 python bench.py --precision bf16x3 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2m_bench_bf16x3.json 2> gpurun_out/r2m_bench_bf16x3.err; echo "bench x3 rc=$?"
+head -c 400 gpurun_out/r2m_bench_bf16x3.json; echo
+timeout 900 python bench.py --precision bf16x6 --steps 2 --warmup 1 --no-cpu-baseline --no-latency > gpurun_out/r2m_bench_bf16x6.json 2> gpurun_out/r2m_bench_bf16x6.err; echo "bench x6 rc=$?"
+head -c 400 gpurun_out/r2m_bench_bf16x6.json; echo
+echo done
