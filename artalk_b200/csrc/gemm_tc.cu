@@ -686,15 +686,20 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
 // RB (EPI 1): residual-chunk buffers per epilogue half. RB = 2 trades one operand stage for two more 16 KB buffers so that two
 // residual TMA loads per half are in flight: for K <= 2048 (the wav2vec out-projection: 16 k-blocks per tile) the epilogue,
 // not the MMA ring, is the critical path and each chunk exposed most of a DRAM round trip (~3 us per 32-column chunk).
-// SPLIT2 (parity-grade modes, operands are bf16 piece blocks): 256 x 128 pair tiles whose accumulator stage holds the main (p0 x p0)
-// and the correction accumulator side by side (2 x 128 columns, as gemm_tc_kernel<.., SPLIT>), two stages = the 512 TMEM columns.
-template <int EPI, int RB = 1, bool SPLIT2 = false>
+// SPLIT2 (parity-grade modes, operands are bf16 piece blocks): an accumulator stage holds the main (p0 x p0) and the correction
+// accumulator side by side (as gemm_tc_kernel<.., SPLIT>). SPLIT2 = 128: 256 x 128 pair tiles, two stages of 2 x 128 columns
+// (shared-memory bound: 24 KB written + 32 KB read per 256-clk k-block, tensor pipe 40-45 %, profiles/r2_ncu_new_kernels.md).
+// SPLIT2 = 256: 256 x 256 tiles, ONE stage of 2 x 256 columns = all of TMEM: the epilogue no longer overlaps the next tile's MMAs,
+// but with K' = 3 K (>= 24 k-blocks of 512 clk) the main loop is 3-6x longer than the epilogue and runs at the 256-wide tile's
+// operand reuse.
+template <int EPI, int RB = 1, int SPLIT2 = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmO, const TcParams p) {
-  constexpr int BN = SPLIT2 ? 128 : 256;
+  constexpr int BN = SPLIT2 ? SPLIT2 : 256;
   constexpr int ACC = SPLIT2 ? 2 * BN : BN;                      // TMEM columns per accumulator stage
+  constexpr int NACC = 512 / ACC;                                // accumulator stages (1 or 2)
   constexpr int NST = EPI == 1 ? STAGES2 - RB : STAGES2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -791,8 +796,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
         const uint32_t idesc = make_idesc_2sm(tile >= p.main_tiles ? p.tail_bn : BN);
-        const int acc = it & 1;
-        mbar_wait(tempty_bar(acc), (((uint32_t)it >> 1) & 1u) ^ 1u, p.err_flag, 0x22);
+        const int acc = it % NACC;
+        mbar_wait(tempty_bar(acc), (((uint32_t)it / NACC) & 1u) ^ 1u, p.err_flag, 0x22);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC);
         int slot = 0;
@@ -850,7 +855,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int col_base, bn, mt, b;
       decode(tile, col_base, bn, mt, b);
       const int n_chunks = bn >> 5;
-      const int acc = it & 1;
+      const int acc = it % NACC;
       const int t_in_batch = mt * 256 + (int)rank * 128 + q * 32 + lane;
       const bool row_ok = t_in_batch < p.rpb;
       const int r = b * p.rpb + t_in_batch;
@@ -865,7 +870,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (p.resid && !p.tma_resid) prefetch_l2(p.resid + r_off + col0);
         }
       }
-      mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 0x24);
+      mbar_wait(tfull_bar(acc), ((uint32_t)it / NACC) & 1u, p.err_flag, 0x24);
       tc_fence_after();
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += 2) {
@@ -985,7 +990,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
   return launch_bn_epi<BN, 0>(tmA, tmW, tmWt, tmO, p, st);
 }
 
-template <int EPI, int RB = 1, bool SPLIT2 = false>
+template <int EPI, int RB = 1, int SPLIT2 = 0>
 int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmR,
                     const CUtensorMap& tmO, const TcParams& p, cudaStream_t st) {
   static int max_clusters_dev[16] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
@@ -1020,7 +1025,8 @@ int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
 int g_tma_out = 2;        // (declared above make_out_map) option "gemm_tma_out": 0 = st.global epilogue, 1 = TMA stores for fp32-only outputs, 2 = also bf16-only outputs
 int g_resid_deep = 1;     // option "gemm_resid_deep": residual buffers per epilogue half beyond one: 1 -> two for K <= 2048, 2 -> also three for K <= 1024
 int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
-int g_pair_split = 1;     // option "gemm_pair_split": parity-grade (piece-block) GEMMs may take the CTA-pair kernel (256 x 128 tiles)
+int g_pair_split = 256;   // option "gemm_pair_split": parity-grade (piece-block) GEMMs take the CTA-pair kernel in 256 x 256 tiles with one
+                          // accumulator stage (256), in 256 x 128 tiles with two (128), or the 1-CTA kernel (0)
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
 }  // namespace
@@ -1062,7 +1068,7 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   const bool pair_split = g.split_acc != 0;
   if (g_pair_mode && (!pair_split || (g_pair_split && (g.K / BK) % g.split_acc == 0)) && !g.tap_w && g.groups == 1 && !g.qkv_mode && g.N >= 256 &&
       g.N % 128 == 0) {
-    const int BN2 = pair_split ? 128 : 256;                        // piece-block GEMMs: main | correction accumulators of 128 columns
+    const int BN2 = (pair_split && g_pair_split == 128) ? 128 : 256;     // piece-block GEMMs: main | correction accumulators side by side
     const int tpb2 = ceil_div(p.rpb, 256), n_tiles_n2 = ceil_div(g.N, BN2), n_cl = g_num_sms / 2;
     const long tiles2 = (long)p.n_batches * tpb2 * n_tiles_n2;
     const double row_eff = (double)p.rpb / ((double)tpb2 * 256.0);
@@ -1116,9 +1122,13 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
         if (t < 0) return AT_ECUDA;
         p.tma_out = t;
       }
+      if (pair_split && BN2 == 128) {
+        if (p.gate || p.resid) return launch_pair_epi<1, 1, 128>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
+        return launch_pair_epi<0, 1, 128>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
+      }
       if (pair_split) {
-        if (p.gate || p.resid) return launch_pair_epi<1, 1, true>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
-        return launch_pair_epi<0, 1, true>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
+        if (p.gate || p.resid) return launch_pair_epi<1, 1, 256>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
+        return launch_pair_epi<0, 1, 256>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       }
       if (p.tma_resid && g_resid_deep >= 2 && p.num_kb <= 16) return launch_pair_epi<1, 3>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (p.tma_resid && g_resid_deep >= 1 && p.num_kb <= 32) return launch_pair_epi<1, 2>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -186,12 +187,14 @@ class BitwiseARModel:
         pinned = t.device.type == "cpu" and t.is_pinned()
         return t.to(self._device, dtype, non_blocking=pinned).contiguous()
 
-    def audio_cond(self, chunks: torch.Tensor) -> torch.Tensor:
-        """(N, 64000) audio chunks -> (N, 181, 1024) conditioning (wav2vec2 + area pooling)."""
+    def audio_cond(self, chunks: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(N, 64000) audio chunks -> (N, 181, 1024) conditioning (wav2vec2 + area pooling); ``out``: optional contiguous
+        (N, 181, 1024) fp32 device tensor to write into."""
         x = self._dev(chunks)
         if x.dim() != 2 or x.shape[1] != self.cfg.chunk_samples:
             raise ValueError("expected (N, %d) chunks, got %s" % (self.cfg.chunk_samples, tuple(x.shape)))
-        cond = torch.empty(x.shape[0], self.cfg.seq_tokens, self.cfg.cond_dim, device=self._device)
+        cond = out if out is not None else torch.empty(x.shape[0], self.cfg.seq_tokens, self.cfg.cond_dim, device=self._device)
+        assert cond.is_contiguous() and cond.dtype == torch.float32 and cond.numel() == x.shape[0] * self.cfg.seq_tokens * self.cfg.cond_dim
         self._call(_lib.lib().artalk_audio_encode, self._handle(), x.data_ptr(), x.shape[0], cond.data_ptr(),
                    _lib.stream_ptr(self._device))
         return cond
@@ -245,10 +248,19 @@ class BitwiseARModel:
         T, n_chunks = cfg.chunk_frames, motion.shape[1]
         nb = b1 - b0
         style = self.style_cond(None if style_motion is None else style_motion[b0:b1], nb)
-        if audio_ready is not None:                       # audio upload in flight on the copy stream (see inference)
-            torch.cuda.current_stream(self._device).wait_event(audio_ready)
-        cond = self.audio_cond(audio[b0:b1].reshape(nb * n_chunks, cfg.chunk_samples)).view(
-            nb, n_chunks, cfg.seq_tokens, cfg.cond_dim)
+        if isinstance(audio_ready, list):
+            # host input uploaded in clip groups on the copy stream (see inference): wav2vec runs group by group as the
+            # uploads land, so only the first group's transfer is exposed
+            assert b0 == 0 and b1 == audio.shape[0]
+            cond = torch.empty(nb, n_chunks, cfg.seq_tokens, cfg.cond_dim, device=self._device)
+            for g0, g1, ev in audio_ready:
+                torch.cuda.current_stream(self._device).wait_event(ev)
+                self.audio_cond(audio[g0:g1].reshape((g1 - g0) * n_chunks, cfg.chunk_samples), out=cond[g0:g1])
+        else:
+            if audio_ready is not None:                   # audio upload in flight on the copy stream (see inference)
+                torch.cuda.current_stream(self._device).wait_event(audio_ready)
+            cond = self.audio_cond(audio[b0:b1].reshape(nb * n_chunks, cfg.chunk_samples)).view(
+                nb, n_chunks, cfg.seq_tokens, cfg.cond_dim)
         if trace is not None:
             trace["cond"][b0:b1].copy_(cond); trace["style"][b0:b1].copy_(style)
         for g0 in range(0, nb, self.max_clips):
@@ -304,11 +316,27 @@ class BitwiseARModel:
                 self._copy_stream = torch.cuda.Stream(device=self._device)
             self._copy_stream.wait_stream(main)
             with torch.cuda.stream(self._copy_stream):
-                audio = audio.to(self._device, torch.float32, non_blocking=True).contiguous()
-                if pad:
-                    audio = torch.cat([audio, audio.new_zeros(B, pad)], dim=-1)
-                audio_ready = torch.cuda.Event()
-                audio_ready.record(self._copy_stream)
+                if audio.dtype == torch.float32 and B * n_chunks > 768 and os.environ.get("ARTALK_UPLOAD_GROUPS", "1") != "0":
+                    # large batches: upload in groups of ~512 chunks, one event per group; wav2vec (which is sub-batched at
+                    # about that size anyway) starts on group 0 while the later groups are still crossing PCIe
+                    gsz = max(1, 512 // n_chunks)
+                    host = audio
+                    audio = torch.empty(B, n_chunks * cfg.chunk_samples, device=self._device, dtype=torch.float32)
+                    if pad:
+                        audio[:, S:].zero_()
+                    audio_ready = []
+                    for g0 in range(0, B, gsz):
+                        g1 = min(B, g0 + gsz)
+                        audio[g0:g1, :S].copy_(host[g0:g1], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(self._copy_stream)
+                        audio_ready.append((g0, g1, ev))
+                else:
+                    audio = audio.to(self._device, torch.float32, non_blocking=True).contiguous()
+                    if pad:
+                        audio = torch.cat([audio, audio.new_zeros(B, pad)], dim=-1)
+                    audio_ready = torch.cuda.Event()
+                    audio_ready.record(self._copy_stream)
             audio.record_stream(main)
         else:
             audio = self._dev(audio)

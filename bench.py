@@ -329,6 +329,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     verts = torch.empty(B * frames, 5023, 3, device=dev) if mesh else None          # 60 KB per frame, stays on the device
     gather = parallel.MotionGather(dev) if world > 1 else None
+    d2h_stream = torch.cuda.Stream(device=dev)
     flame_ev = []
 
     def decode_mesh(m, timed_events=False):
@@ -353,10 +354,16 @@ def main():
         # pinned host buffers straight into the public call: it uploads the style clips, runs the style encoder while the
         # audio upload proceeds on its copy stream, then wav2vec waits for the upload; the result (motion) goes back to the host
         m = eng.inference_batch(audio_host, style_host)
+        # the motion goes back to the host on a side stream while the mesh decode (which leaves its vertices on the device) runs
+        main = torch.cuda.current_stream(dev)
+        d2h_stream.wait_stream(main)
+        with torch.cuda.stream(d2h_stream):
+            out_host.copy_(m, non_blocking=True)
+        m.record_stream(d2h_stream)
         decode_mesh(m)
         if gather is not None:
             gather.start(m, world * B)
-        out_host.copy_(m, non_blocking=True)
+        main.wait_stream(d2h_stream)                     # the step ends when the result is on the host
         return m
 
     def timed(fn, steps, warmup):

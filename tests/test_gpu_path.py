@@ -337,6 +337,20 @@ def test_pinned_host_audio_equals_device_audio():
         assert torch.equal(ref, got)
 
 
+def test_pinned_host_audio_uploaded_in_groups():
+    """Large pinned batches (> 768 chunks) cross PCIe in clip groups, one event per group, and wav2vec consumes them group by group
+    (model.inference): same result as one device-resident call; ragged clip length (zero-padded tail on the device)."""
+    m = model("TINY", "bf16")
+    B, S = 390, 100000                                               # 2 chunks per clip, 780 chunks: groups of 256 and 134 clips
+    a = synthetic.make_audio(4, S).repeat(98, 1)[:B].contiguous()
+    a[5] *= 0.5; a[300] *= 0.25                                      # clips in different groups that differ from their neighbours
+    s = synthetic.make_style_motion(2).repeat(195, 1, 1).contiguous()
+    ref = m.inference({"audio": a.to(DEV), "style_motion": s.to(DEV)})
+    got = m.inference({"audio": a.pin_memory(), "style_motion": s.pin_memory()})
+    assert got.shape == ref.shape == (B, 157, 106)
+    assert torch.equal(ref, got)
+
+
 def test_clip_subbatching_and_empty():
     case = CASES["tiny_style"]
     m = model("TINY", "fp32")
