@@ -188,6 +188,8 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "gemm_force_bn")) { set_gemm_force_bn(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_resid_deep")) { set_gemm_resid_deep(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_pair_split")) { set_gemm_pair_split(value); return AT_OK; }
+  if (!std::strcmp(name, "gemm_pair_min_waves10")) { set_gemm_pair_min_waves10(value); return AT_OK; }
+  if (!std::strcmp(name, "gemm_pair_qkv")) { set_gemm_pair_qkv(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_tma_out")) { set_gemm_tma_out(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_band_mb")) { set_gemm_band_mb(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_tma_resid")) { set_gemm_tma_resid(value); return AT_OK; }

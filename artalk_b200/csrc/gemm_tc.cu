@@ -377,6 +377,69 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, uint32_t taddr, boo
     }
 }
 
+// Fused AR q/k/v epilogue (app/transformer.py:68-74) of one 32-row warp: a warp owns whole heads (64 columns = 2 TMEM chunks), heads
+// alternate between the two warp halves; q and k heads are L2-normalised (q additionally scaled by head_scale), q -> qbuf[row],
+// k / v -> the caches at kv_map(row) (+ layer stride). `trow` = TMEM address of the warp's lanes at the accumulator's column 0.
+// Shared by the 1-CTA and the CTA-pair kernels. All 32 lanes must call it.
+__device__ __forceinline__ void epi_qkv(const TcParams& p, uint32_t trow, int bn, int col_base, int half, bool row_ok, int r,
+                                        const float* bias, float4* scr, int lane) {
+  const int period = (p.qkv_mode == 1 ? 3 : 2) * p.qkv_C;
+#pragma unroll 1
+  for (int hd = half; hd < (bn >> 6); hd += 2) {
+    float a[32], b2[32];
+    tmem_ld32(trow + (uint32_t)(hd * 64), a);
+    tmem_ld32(trow + (uint32_t)(hd * 64 + 32), b2);
+    const int col0 = col_base + hd * 64;
+    if (col0 >= p.N) continue;                                   // warp-uniform
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+        float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 32 + j));
+        a[j] += b0.x; a[j + 1] += b0.y; a[j + 2] += b0.z; a[j + 3] += b0.w;
+        b2[j] += b1.x; b2[j + 1] += b1.y; b2[j + 2] += b1.z; b2[j + 3] += b1.w;
+      }
+    }
+    const int layer = col0 / period, o = col0 - layer * period;
+    const int sec = o / p.qkv_C, hc = o - sec * p.qkv_C;
+    const bool is_q = (p.qkv_mode == 1 && sec == 0);
+    const bool is_k = (p.qkv_mode == 1) ? (sec == 1) : (sec == 0);
+    float scale = 1.0f;
+    if (is_q || is_k) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ss = fmaf(a[j], a[j], fmaf(b2[j], b2[j], ss));
+      scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);                     // F.normalize eps
+      if (is_q) scale *= p.head_scale[hc >> 6];
+    }
+    // the head's 32 rows x 128 B leave through the warp's scratch so that every store instruction covers 4 full lines
+    bf16* dst = is_q ? p.qbuf + hc : (is_k ? p.kcache : p.vcache) + (int64_t)layer * p.kv_layer_stride + hc;
+    const int64_t row_off = !row_ok ? 0 : (is_q ? (int64_t)r * p.qkv_C : p.kv_map.off(r));
+    uint4* scr4 = reinterpret_cast<uint4*>(scr);
+    const int sw = lane & 7;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const float* src = ch < 4 ? &a[ch * 8] : &b2[(ch - 4) * 8];
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(src[0] * scale, src[1] * scale), h1 = __floats2bfloat162_rn(src[2] * scale, src[3] * scale);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(src[4] * scale, src[5] * scale), h3 = __floats2bfloat162_rn(src[6] * scale, src[7] * scale);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      scr4[lane * 8 + (ch ^ sw)] = pk;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it2 = 0; it2 < 8; ++it2) {
+      const int j = it2 * 4 + (lane >> 3), ch = lane & 7;
+      const int64_t off_j = __shfl_sync(0xffffffffu, row_off, j);
+      const bool ok_j = __shfl_sync(0xffffffffu, (int)row_ok, j) != 0;
+      const uint4 val = scr4[j * 8 + (ch ^ (j & 7))];
+      if (ok_j) *reinterpret_cast<uint4*>(dst + off_j + ch * 8) = val;
+    }
+    __syncwarp();
+  }
+}
+
 // EPI: 0 = bias/activation only, 1 = gate and/or residual operands, 2 = fused AR q/k/v epilogue
 // SPLIT (parity-grade mode, operands are bf16 piece blocks, split.cu): the tensor core adds every MMA into its fp32 accumulator
 // with truncation, a relative loss of ~2^-24 per instruction that grows with the chain length (measured: 1e-4 relative at
@@ -547,65 +610,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), ((uint32_t)it >> 1) & 1u, p.err_flag, 4);
       tc_fence_after();
       if constexpr (EPI == 2) {
-        // fused AR q/k/v epilogue: a warp owns whole heads (64 columns = 2 TMEM chunks), heads alternate between the halves
-        {
-          const int period = (p.qkv_mode == 1 ? 3 : 2) * p.qkv_C;
-#pragma unroll 1
-          for (int hd = half; hd < (bn >> 6); hd += 2) {
-            float a[32], b2[32];
-            const uint32_t tcol = (uint32_t)(acc * ACC_COLS + hd * 64);
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol, a);
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + 32, b2);
-            const int col0 = col_base + hd * 64;
-            if (col0 >= p.N) continue;                                   // warp-uniform
-            if (bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-                float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 32 + j));
-                a[j] += b0.x; a[j + 1] += b0.y; a[j + 2] += b0.z; a[j + 3] += b0.w;
-                b2[j] += b1.x; b2[j + 1] += b1.y; b2[j + 2] += b1.z; b2[j + 3] += b1.w;
-              }
-            }
-            const int layer = col0 / period, o = col0 - layer * period;
-            const int sec = o / p.qkv_C, hc = o - sec * p.qkv_C;
-            const bool is_q = (p.qkv_mode == 1 && sec == 0);
-            const bool is_k = (p.qkv_mode == 1) ? (sec == 1) : (sec == 0);
-            float scale = 1.0f;
-            if (is_q || is_k) {
-              float ss = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) ss = fmaf(a[j], a[j], fmaf(b2[j], b2[j], ss));
-              scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);                     // F.normalize eps
-              if (is_q) scale *= p.head_scale[hc >> 6];
-            }
-            // the head's 32 rows x 128 B leave through the warp's scratch so that every store instruction covers 4 full lines
-            bf16* dst = is_q ? p.qbuf + hc : (is_k ? p.kcache : p.vcache) + (int64_t)layer * p.kv_layer_stride + hc;
-            const int64_t row_off = !row_ok ? 0 : (is_q ? (int64_t)r * p.qkv_C : p.kv_map.off(r));
-            uint4* scr4 = reinterpret_cast<uint4*>(scr);
-            const int sw = lane & 7;
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              const float* src = ch < 4 ? &a[ch * 8] : &b2[(ch - 4) * 8];
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(src[0] * scale, src[1] * scale), h1 = __floats2bfloat162_rn(src[2] * scale, src[3] * scale);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(src[4] * scale, src[5] * scale), h3 = __floats2bfloat162_rn(src[6] * scale, src[7] * scale);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              scr4[lane * 8 + (ch ^ sw)] = pk;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int it2 = 0; it2 < 8; ++it2) {
-              const int j = it2 * 4 + (lane >> 3), ch = lane & 7;
-              const int64_t off_j = __shfl_sync(0xffffffffu, row_off, j);
-              const bool ok_j = __shfl_sync(0xffffffffu, (int)row_ok, j) != 0;
-              const uint4 val = scr4[j * 8 + (ch ^ (j & 7))];
-              if (ok_j) *reinterpret_cast<uint4*>(dst + off_j + ch * 8) = val;
-            }
-            __syncwarp();
-          }
-        }
+        epi_qkv(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS), bn, col_base, half, row_ok, r, bias, scr, lane);
       } else {
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += 2)
@@ -847,7 +852,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
     float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 1024u - smem_u32(smem_raw)) + (warp - 4) * 4096);
-    const CUtensorMap* tmo = p.tma_out ? &tmO : nullptr;
+    const CUtensorMap* tmo = (EPI != 2 && p.tma_out) ? &tmO : nullptr;
     int it = 0;
     uint32_t r_use = 0;
     pdl_wait();
@@ -872,6 +877,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       mbar_wait(tfull_bar(acc), ((uint32_t)it / NACC) & 1u, p.err_flag, 0x24);
       tc_fence_after();
+      if constexpr (EPI == 2) {
+        epi_qkv(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC), bn, col_base, half, row_ok, r, p.bias, scr, lane);
+      } else
 #pragma unroll 1
       for (int c = half; c < n_chunks; c += 2) {
         const float4* rsm = nullptr;
@@ -1027,6 +1035,8 @@ int g_resid_deep = 1;     // option "gemm_resid_deep": residual buffers per epil
 int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
 int g_pair_split = 256;   // option "gemm_pair_split": parity-grade (piece-block) GEMMs take the CTA-pair kernel in 256 x 256 tiles with one
                           // accumulator stage (256), in 256 x 128 tiles with two (128), or the 1-CTA kernel (0)
+int g_pair_min_waves10 = 18;   // option "gemm_pair_min_waves10": the pair kernel needs at least this many tenths of a wave of 256-row tiles (was 40: 256 x 30 s step 590.0 -> 579.8 ms, bit-identical)
+int g_pair_qkv = 1;       // option "gemm_pair_qkv": the fused q/k/v epilogue GEMMs may take the CTA-pair kernel
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
 }  // namespace
@@ -1038,6 +1048,8 @@ void set_gemm_band_mb(int mb) { g_band_mb = mb; }
 void set_gemm_tma_out(int on) { g_tma_out = on; }
 void set_gemm_resid_deep(int on) { g_resid_deep = on; }
 void set_gemm_pair_split(int on) { g_pair_split = on; }
+void set_gemm_pair_min_waves10(int v) { g_pair_min_waves10 = v; }
+void set_gemm_pair_qkv(int v) { g_pair_qkv = v; }
 
 int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   GemmArgs g = g_in;
@@ -1064,9 +1076,9 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   p.n_batches = batched ? ceil_div(g.M, g.a_map.rpb) : 1;
   AT_REQUIRE(!batched || g.M % g.a_map.rpb == 0, "gemm_tc: M must be a multiple of the A view's rows per batch");
   p.tiles_per_batch = ceil_div(p.rpb, BM);
-  // CTA-pair kernel (256x256 tiles over two SMs) for the large plain GEMMs: >= 4 waves of pair tiles at >= 85 % wave efficiency
+  // CTA-pair kernel (256x256 tiles over two SMs) for the large GEMMs: >= 1.8 waves of pair tiles at >= 85 % wave efficiency
   const bool pair_split = g.split_acc != 0;
-  if (g_pair_mode && (!pair_split || (g_pair_split && (g.K / BK) % g.split_acc == 0)) && !g.tap_w && g.groups == 1 && !g.qkv_mode && g.N >= 256 &&
+  if (g_pair_mode && (!pair_split || (g_pair_split && (g.K / BK) % g.split_acc == 0)) && !g.tap_w && g.groups == 1 && (!g.qkv_mode || (g_pair_qkv && !pair_split)) && g.N >= 256 &&
       g.N % 128 == 0) {
     const int BN2 = (pair_split && g_pair_split == 128) ? 128 : 256;     // piece-block GEMMs: main | correction accumulators side by side
     const int tpb2 = ceil_div(p.rpb, 256), n_tiles_n2 = ceil_div(g.N, BN2), n_cl = g_num_sms / 2;
@@ -1075,9 +1087,9 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
     // ragged last wave: its tiles are cut into column slices (>= 32 wide) that run side by side on the idle CTA pairs
     const int rem2 = (int)(tiles2 % n_cl);
     int split2 = 1;
-    if (rem2 > 0) while (BN2 / (split2 * 2) >= 32 && rem2 * split2 * 2 <= n_cl) split2 *= 2;
+    if (rem2 > 0) while (BN2 / (split2 * 2) >= (g.qkv_mode ? 64 : 32) && rem2 * split2 * 2 <= n_cl) split2 *= 2;     // q/k/v epilogue: whole heads
     const double waves_eff = (double)(tiles2 / n_cl) + (rem2 ? (split2 > 1 ? 1.3 / split2 : 1.0) : 0.0);
-    if (tiles2 >= 4L * n_cl && (double)tiles2 / (waves_eff * n_cl) >= 0.85 && row_eff >= 0.85 && tiles2 < (1L << 30)) {
+    if (10L * tiles2 >= (long)g_pair_min_waves10 * n_cl && (double)tiles2 / (waves_eff * n_cl) >= 0.85 && row_eff >= 0.85 && tiles2 < (1L << 30)) {
       p.tiles_per_batch = tpb2; p.n_tiles_n = n_tiles_n2; p.groups = 1;
       if (g_band_mb > 0 && (double)g.N * g.K * 2.0 > 2.0 * g_band_mb * 1048576.0) {
         const int bn_tiles = (int)((double)g_band_mb * 1048576.0 / ((double)BN2 * g.K * 2.0));
@@ -1091,8 +1103,17 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
       p.gate = g.gate; p.gate_dt = g.gate_dt; p.gate_map = g.gate_map; p.resid = g.resid; p.resid_map = g.resid_map;
       p.out32 = g.out32; p.out_act = g.out_act; p.out_act_dt = g.out_act_dt; p.c_map = g.c_map;
       p.err_flag = g_err_flag;
-      p.qkv_mode = 0; p.qkv_C = 0; p.head_scale = nullptr; p.qbuf = nullptr; p.kcache = nullptr; p.vcache = nullptr;
-      p.kv_map = g.kv_map; p.kv_layer_stride = 0;
+      p.qkv_mode = g.qkv_mode; p.qkv_C = g.qkv_C; p.head_scale = g.head_scale; p.qbuf = (bf16*)g.qbuf; p.kcache = (bf16*)g.kcache;
+      p.vcache = (bf16*)g.vcache; p.kv_map = g.kv_map; p.kv_layer_stride = g.kv_layer_stride;
+      if (g.qkv_mode) {
+        AT_REQUIRE((g.qkv_mode == 1 || g.qkv_mode == 2) && g.qkv_C > 0 && g.qkv_C % 64 == 0 && g.N % 64 == 0 &&
+                   g.N % ((g.qkv_mode == 1 ? 3 : 2) * g.qkv_C) == 0, "gemm_tc: bad fused q/k/v shape (N=%d C=%d)", g.N, g.qkv_C);
+        AT_REQUIRE(g.kcache && g.vcache && (g.qkv_mode == 2 || (g.qbuf && g.head_scale)) && g.act == ACT_NONE && !g.gate && !g.resid,
+                   "gemm_tc: bad fused q/k/v arguments");
+        AT_REQUIRE(g.kv_map.rs % 8 == 0 && g.kv_map.bs % 8 == 0 && g.kv_layer_stride % 8 == 0 && ((uintptr_t)g.kcache % 16 == 0) &&
+                   ((uintptr_t)g.vcache % 16 == 0) && (!g.qbuf || (uintptr_t)g.qbuf % 16 == 0) &&
+                   (!g.bias || ((uintptr_t)g.bias % 16 == 0)), "gemm_tc: fused q/k/v outputs must be 16-byte aligned");
+      }
       bool v = (g.c_map.rs % 8 == 0) && (g.c_map.bs % 8 == 0);
       if (g.bias) v = v && (((uintptr_t)g.bias) % 16 == 0);
       if (g.gate) v = v && (g.gate_map.rs % 8 == 0) && (g.gate_map.bs % 8 == 0) && (((uintptr_t)g.gate) % 16 == 0);
@@ -1122,6 +1143,7 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
         if (t < 0) return AT_ECUDA;
         p.tma_out = t;
       }
+      if (g.qkv_mode) return launch_pair_epi<2>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (pair_split && BN2 == 128) {
         if (p.gate || p.resid) return launch_pair_epi<1, 1, 128>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
         return launch_pair_epi<0, 1, 128>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);

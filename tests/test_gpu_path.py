@@ -12,7 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from artalk_b200 import config, synthetic  # noqa: E402
+from artalk_b200 import _lib, config, synthetic  # noqa: E402
 from artalk_b200.model import BitwiseARModel, unpack_words, pack_words  # noqa: E402
 from artalk_b200.flame import FLAMEModel  # noqa: E402
 from artalk_b200.engine import ARTAvatarInferEngine, smooth_motion  # noqa: E402
@@ -335,6 +335,23 @@ def test_pinned_host_audio_equals_device_audio():
     for _ in range(3):
         got = m.inference({"audio": ah, "style_motion": sh})
         assert torch.equal(ref, got)
+
+
+def test_pair_kernel_qkv_epilogue_is_bit_identical():
+    """The fused q/k/v epilogue (head norms + KV-cache scatter) runs in the CTA-pair GEMM kernel when a scale step has enough rows
+    (48 clips: 4800 rows at the finest scale = 171 pair tiles) and in the 1-CTA kernel otherwise: same accumulation order, same
+    epilogue code, so the free-running output is bit-identical with the pair path switched off."""
+    m = model("TINY", "bf16")
+    a = synthetic.make_audio(48, 64000)
+    s = synthetic.make_style_motion(48)
+    outs = []
+    try:
+        for on in (1, 0):
+            _lib.check(_lib.lib().artalk_set_option(b"gemm_pair_qkv", on))
+            outs.append(m.inference({"audio": a, "style_motion": s}).clone())
+    finally:
+        _lib.check(_lib.lib().artalk_set_option(b"gemm_pair_qkv", 1))
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_pinned_host_audio_uploaded_in_groups():
