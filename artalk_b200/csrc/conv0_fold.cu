@@ -8,7 +8,10 @@
 //   out_c           = gelu(rstd . (wq_c . x + bq_c) + beta_c),   wq = wc * gamma, bq = bc * gamma
 // i.e. 132 FMAs per FRAME for the statistics instead of a mean / centred-square / normalise pass per ELEMENT, and no cross-lane
 // reduction, so a thread can own 4 channels for many frames with its filters in registers. The per-element work (10 FMA conv,
-// 1 FMA normalise, erf-GELU) runs on packed pairs (fma.rn.f32x2 -> FFMA2: two channels per instruction).
+// 1 FMA normalise, erf-GELU) runs on packed pairs (fma.rn.f32x2 -> FFMA2: two channels per instruction): 12.5 issued
+// instructions per element. Measured (ncu, profiles/r2_ncu_new_kernels.md): 1.6x faster than the direct kernel, issue 48 %,
+// FMA pipe 27 %; FFMA2 halves the issue slots of the arithmetic but occupies the FMA pipe like two FFMAs, and a third block
+// per SM (80 registers) measured equal.
 // The previous kernel (norms.cu conv0_reg_kernel: one warp per frame, ~31 issued instructions per element at 57 % issue
 // utilisation, profiles/r2_ncu_kernel_table.md) stays for the fp32 / parity-grade modes and as the A/B reference (option "conv0_fold").
 // The sum of squares is evaluated with the same conditioning as the direct form (every term is a dot product with x).
