@@ -162,8 +162,6 @@ def lib() -> C.CDLL:
             l.artalk_set_option(b"posconv4", int(os.environ["ARTALK_POSCONV4"]))
         if os.environ.get("ARTALK_ATTN_BLK"):              # 0: 257..384-key launches take the split-key mode of attn_tc_kernel (A/B switch)
             l.artalk_set_option(b"attn_blk", int(os.environ["ARTALK_ATTN_BLK"]))
-        if os.environ.get("ARTALK_ATTN_POLY"):
-            l.artalk_set_option(b"attn_poly", int(os.environ["ARTALK_ATTN_POLY"]))
         if os.environ.get("ARTALK_SKINNY_TOKENS"):
             l.artalk_set_option(b"skinny_tokens", int(os.environ["ARTALK_SKINNY_TOKENS"]))
         if os.environ.get("ARTALK_GEMM_PAIR", "1") == "0":

@@ -199,7 +199,6 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "posconv4")) { g_posconv4 = value; return AT_OK; }
   if (!std::strcmp(name, "conv0_fold")) { g_conv0_fold = value; return AT_OK; }
   if (!std::strcmp(name, "attn_split")) { g_attn_split = value; return AT_OK; }
-  if (!std::strcmp(name, "attn_poly")) { set_attn_poly(value); return AT_OK; }
   if (!std::strcmp(name, "attn_blk")) { set_attn_blk(value); return AT_OK; }
   if (!std::strcmp(name, "w2v_graph_chunks")) { g_w2v_graph_chunks = value; return AT_OK; }
   if (!std::strcmp(name, "skinny_max_m")) { set_skinny_max_m(value); return AT_OK; }

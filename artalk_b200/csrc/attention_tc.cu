@@ -73,19 +73,6 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// exp2 on the FMA / integer pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5] (magic-number rounding), 2^f by a
-// degree-3 polynomial (max relative error 7.7e-5, far below the bf16 rounding of P, 3.9e-3), n added to the exponent field.
-// The softmax loop is bound by the 16 ex2 per clock of the MUFU unit (26 600 per 128 x 208 tile); sending a fraction of the
-// elements through this path balances the two pipes (option "attn_poly").
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;                     // 1.5 * 2^23: the low mantissa bits of t hold round(x)
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(0.05508868396282196f, f, 0.24260404706001282f);
-  p = fmaf(p, f, 0.6932762265205383f);
-  p = fmaf(p, f, 0.9999289512634277f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 // MN-major operand tile (V: rows = keys (K dim), 64 contiguous head dims = one 128 B swizzle row):
 // canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> 8-key groups 1024 B apart (SBO); a single 64-wide N block
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
@@ -100,14 +87,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// POLY: 0 = every exponential on the MUFU unit, 1 = one in four on the FMA pipe (ex2_poly), 2 = one in two
 // SPLIT (parity-grade mode "bf16x3", fp32 data flow): Q, K, V arrive as two bf16 pieces each (x = hi + lo, planes of one tensor)
 // and both contractions keep the three piece products hi.hi + lo.hi + hi.lo (relative error ~2^-16 per product, as the split
 // GEMMs): S = Qh Kh^T + Ql Kh^T + Qh Kl^T in one accumulator; P is split in registers and written IN PLACE over the 16 S columns
 // just read (hi pieces in the first 8 columns, lo pieces in the last 8), so the three MMA-2 products take their A operands from
 // TMEM without extra columns; O = Ph Vh + Pl Vh + Ph Vl lives outside the S range (columns 192..255 of buffer 0) and leaves as
 // fp32. One stage of operands fills shared memory, so SPLIT launches always run in split-key mode (one item per CTA at a time).
-template <int POLY, bool SPLIT = false>
+template <bool SPLIT = false>
 __global__ void __launch_bounds__(384, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
@@ -331,7 +317,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int j = 0; j < 16; j += 2) {
               const float x0 = fmaf(__uint_as_float(s0[j]), p.scale_log2e, -ms), x1 = fmaf(__uint_as_float(s0[j + 1]), p.scale_log2e, -ms);
               const float p0 = ex2(x0);
-              const float p1 = (POLY == 2 || (POLY == 1 && (j & 2))) ? ex2_poly(x1) : ex2(x1);      // compile-time choice per element
+              const float p1 = ex2(x1);
               sum2[(j >> 1) & 1] += p0 + p1;
               __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
               pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
@@ -730,8 +716,6 @@ int make_map(CUtensorMap* m, const void* base, uint64_t width, uint64_t rows, ui
 
 int g_attn_blk = 1;        // option "attn_blk": bounded AR attention over 257..384 keys takes the block-wise kernel (one item per warpgroup)
 void set_attn_blk(int v) { g_attn_blk = v; }
-int g_attn_poly = 0;       // option "attn_poly": share of the softmax exponentials computed on the FMA pipe (0, 1 = 1/4, 2 = 1/2)
-void set_attn_poly(int v) { g_attn_poly = v < 0 ? 0 : (v > 2 ? 2 : v); }
 
 // parity-grade launches (AttnArgs::split_planes): two key halves of 16..192 keys, one stage of hi + lo tiles in shared memory
 bool attention_tc_split_supported(int lq, int lk, int head_dim) {
@@ -754,10 +738,8 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   AT_TRY(dev_ctx(&dc));
   const int g_num_sms = dc->num_sms;
   unsigned int* const g_err_flag = dc->err_flag;
-  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<0>, SMEM_LIMIT));
-  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<1>, SMEM_LIMIT));
-  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<2>, SMEM_LIMIT));
-  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<0, true>, SMEM_LIMIT));
+  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<false>, SMEM_LIMIT));
+  AT_TRY(ensure_dyn_smem((const void*)attn_tc_kernel<true>, SMEM_LIMIT));
   const bool split = a.split_planes != 0;
   AT_REQUIRE(!split || (attention_tc_split_supported(a.lq, a.lk, a.head_dim) && a.q_ss > 0 && a.k_ss > 0 && a.v_ss > 0 && a.o_rs % 4 == 0 &&
                         a.o_ss % 4 == 0), "attention_tc: unsupported split launch (lq=%d lk=%d)", a.lq, a.lk);
@@ -797,7 +779,7 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   const int grid = p.total_items < g_num_sms ? p.total_items : g_num_sms;
   g_trace_dims[0] = a.n_seq * a.n_heads; g_trace_dims[1] = a.lq; g_trace_dims[2] = a.lk;
   if (split) {
-    AT_CUDA(launch_k(attn_tc_kernel<0, true>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
+    AT_CUDA(launch_k(attn_tc_kernel<true>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
     AT_LAUNCH_CHECK();
     return AT_OK;
   }
@@ -808,9 +790,7 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
     AT_LAUNCH_CHECK();
     return AT_OK;
   }
-  if (g_attn_poly == 2) AT_CUDA(launch_k(attn_tc_kernel<2>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
-  else if (g_attn_poly == 1) AT_CUDA(launch_k(attn_tc_kernel<1>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
-  else AT_CUDA(launch_k(attn_tc_kernel<0>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
+  AT_CUDA(launch_k(attn_tc_kernel<false>, dim3(grid), dim3(384), smem, st, tmQ, tmK, tmV, tmK2, tmV2, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }

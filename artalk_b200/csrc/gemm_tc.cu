@@ -691,12 +691,12 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
 // RB (EPI 1): residual-chunk buffers per epilogue half. RB = 2 trades one operand stage for two more 16 KB buffers so that two
 // residual TMA loads per half are in flight: for K <= 2048 (the wav2vec out-projection: 16 k-blocks per tile) the epilogue,
 // not the MMA ring, is the critical path and each chunk exposed most of a DRAM round trip (~3 us per 32-column chunk).
-// SPLIT2 (parity-grade modes, operands are bf16 piece blocks): an accumulator stage holds the main (p0 x p0) and the correction
-// accumulator side by side (as gemm_tc_kernel<.., SPLIT>). SPLIT2 = 128: 256 x 128 pair tiles, two stages of 2 x 128 columns
-// (shared-memory bound: 24 KB written + 32 KB read per 256-clk k-block, tensor pipe 40-45 %, profiles/r2_ncu_new_kernels.md).
-// SPLIT2 = 256: 256 x 256 tiles, ONE stage of 2 x 256 columns = all of TMEM: the epilogue no longer overlaps the next tile's MMAs,
-// but with K' = 3 K (>= 24 k-blocks of 512 clk) the main loop is 3-6x longer than the epilogue and runs at the 256-wide tile's
-// operand reuse.
+// SPLIT2 = 256 (parity-grade modes, operands are bf16 piece blocks): the accumulator stage holds the main (p0 x p0) and the correction
+// accumulator side by side (as gemm_tc_kernel<.., SPLIT>): 256 x 256 tiles, ONE stage of 2 x 256 columns = all of TMEM. The
+// epilogue no longer overlaps the next tile's MMAs, but with K' = 3 K (>= 24 k-blocks of 512 clk) the main loop is 3-6x longer
+// than the epilogue and runs at the 256-wide tile's operand reuse. (A 256 x 128 variant with two stages measured 10 % slower on
+// the whole bf16x3 step: with N = 128 a k-block moves 24 KB into and 32 KB out of shared memory per 256 clk, tensor pipe 40-45 %,
+// profiles/r2_ncu_new_kernels.md.)
 template <int EPI, int RB = 1, int SPLIT2 = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -1033,8 +1033,7 @@ int g_tma_resid = 1;      // developer switch (option "gemm_tma_resid")
 int g_tma_out = 2;        // (declared above make_out_map) option "gemm_tma_out": 0 = st.global epilogue, 1 = TMA stores for fp32-only outputs, 2 = also bf16-only outputs
 int g_resid_deep = 1;     // option "gemm_resid_deep": residual buffers per epilogue half beyond one: 1 -> two for K <= 2048, 2 -> also three for K <= 1024
 int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is walked in L2 bands of this size (0 = off)
-int g_pair_split = 256;   // option "gemm_pair_split": parity-grade (piece-block) GEMMs take the CTA-pair kernel in 256 x 256 tiles with one
-                          // accumulator stage (256), in 256 x 128 tiles with two (128), or the 1-CTA kernel (0)
+int g_pair_split = 1;     // option "gemm_pair_split": parity-grade (piece-block) GEMMs take the CTA-pair kernel (0: the 1-CTA kernel)
 int g_pair_min_waves10 = 18;   // option "gemm_pair_min_waves10": the pair kernel needs at least this many tenths of a wave of 256-row tiles (was 40: 256 x 30 s step 590.0 -> 579.8 ms, bit-identical)
 int g_pair_qkv = 1;       // option "gemm_pair_qkv": the fused q/k/v epilogue GEMMs may take the CTA-pair kernel
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
@@ -1080,7 +1079,7 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   const bool pair_split = g.split_acc != 0;
   if (g_pair_mode && (!pair_split || (g_pair_split && (g.K / BK) % g.split_acc == 0)) && !g.tap_w && g.groups == 1 && (!g.qkv_mode || (g_pair_qkv && !pair_split)) && g.N >= 256 &&
       g.N % 128 == 0) {
-    const int BN2 = (pair_split && g_pair_split == 128) ? 128 : 256;     // piece-block GEMMs: main | correction accumulators side by side
+    const int BN2 = 256;
     const int tpb2 = ceil_div(p.rpb, 256), n_tiles_n2 = ceil_div(g.N, BN2), n_cl = g_num_sms / 2;
     const long tiles2 = (long)p.n_batches * tpb2 * n_tiles_n2;
     const double row_eff = (double)p.rpb / ((double)tpb2 * 256.0);
@@ -1144,10 +1143,6 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
         p.tma_out = t;
       }
       if (g.qkv_mode) return launch_pair_epi<2>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
-      if (pair_split && BN2 == 128) {
-        if (p.gate || p.resid) return launch_pair_epi<1, 1, 128>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
-        return launch_pair_epi<0, 1, 128>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
-      }
       if (pair_split) {
         if (p.gate || p.resid) return launch_pair_epi<1, 1, 256>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
         return launch_pair_epi<0, 1, 256>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);

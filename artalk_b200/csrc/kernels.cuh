@@ -144,7 +144,6 @@ bool attention_split_supported(const AttnArgs& a);
 size_t attention_split_scratch_bytes(const AttnArgs& a);
 int launch_attention_split(const AttnArgs& a, void* scratch, cudaStream_t st);
 void set_attn_simt_max_lq(int v);
-void set_attn_poly(int v);
 void set_attn_blk(int v);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 // AR q/k/v post-processing (app/transformer.py:71-74): per-head L2 normalise q (x exp(min(scale_mul, ln100))) and k,

@@ -15,9 +15,6 @@ def dev():
     return torch.device("cuda:0")
 
 
-ATTN_POLY_DEFAULT = 0          # library default of option "attn_poly" (tests that toggle it restore this)
-
-
 def rowmap(rpb=0, bs=0, rs=0):
     return _lib.RowMap(rpb, bs, rs)
 
@@ -455,26 +452,6 @@ def test_attention(dt, tol, n_seq, H, D, lq, lk, split):
     out.fill_(float("nan"))
     run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), scale, split)
     _check_attn(out, q, k, v, n_seq, H, D, lq, lk, scale, split, tol)
-
-
-@pytest.mark.parametrize("poly", [1, 2])
-@pytest.mark.parametrize("n_seq,H,lq,lk,split", [(3, 16, 199, 199, 0), (2, 8, 200, 200, 100), (2, 12, 100, 362, 0)])
-def test_attention_polynomial_exp2(poly, n_seq, H, lq, lk, split):
-    """Option attn_poly: one in four / one in two softmax exponentials run on the FMA pipe (degree-3 exp2, 7.7e-5 relative)
-    instead of the MUFU unit; same tolerance against the fp32 reference as the MUFU-only kernel."""
-    D = 64
-    g = torch.Generator(device="cpu").manual_seed(lq + 7 * lk)
-    Cw = H * D
-    q = torch.randn(n_seq, lq, Cw, generator=g).to(dev(), torch.bfloat16)
-    k = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), torch.bfloat16)
-    v = torch.randn(n_seq, lk, Cw, generator=g).to(dev(), torch.bfloat16)
-    out = torch.full((n_seq, lq, Cw), float("nan"), device=dev(), dtype=torch.bfloat16)
-    _lib.check(_lib.lib().artalk_set_option(b"attn_poly", poly))
-    try:
-        run_attn(q, k, v, out, n_seq, H, D, lq, lk, (lq * Cw, Cw, lk * Cw, Cw, lk * Cw, Cw, lq * Cw, Cw), 0.3, split)
-    finally:
-        _lib.check(_lib.lib().artalk_set_option(b"attn_poly", ATTN_POLY_DEFAULT))
-    _check_attn(out, q, k, v, n_seq, H, D, lq, lk, 0.3, split, 2e-2)
 
 
 @pytest.mark.parametrize("n_seq,H,lq,lk", [(4, 12, 25, 212), (5, 12, 1, 182), (2, 12, 100, 362), (3, 12, 50, 262), (7, 12, 5, 187)])

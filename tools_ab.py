@@ -1,5 +1,5 @@
 """Developer tool: same-process, interleaved A/B of process-wide options on the bench step (no mesh, device-resident inputs).
-  python tools_ab.py --clips 64 --seconds 10 --rounds 3 attn_bound=0 attn_bound=1 attn_poly=1 attn_poly=2
+  python tools_ab.py --clips 64 --seconds 10 --rounds 3 base attn_bound=0 attn_blk=0
 Every option spec is `name=value[,name=value...]`; the first spec is the baseline. Options are reset to the library defaults
 (DEFAULTS below) before each spec is applied. Chunk graphs are re-captured after an option change (option epoch)."""
 import argparse, json, os, sys
@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from artalk_b200 import _lib, config, synthetic
 from artalk_b200.engine import ARTAvatarInferEngine
 
-DEFAULTS = {"attn_bound": 1, "attn_poly": 0, "w2v_graph_chunks": 4, "skinny_tokens": 1, "pdl_mask": 3, "gemm_pair": 1, "gemm_tma_out": 2, "gemm_band_mb": 32, "posconv4": 1, "conv0_fold": 1, "attn_blk": 1, "attn_split": 1, "gemm_pair_split": 256, "gemm_pair_min_waves10": 18, "gemm_pair_qkv": 1}
+DEFAULTS = {"attn_bound": 1, "w2v_graph_chunks": 4, "skinny_tokens": 1, "pdl_mask": 3, "gemm_pair": 1, "gemm_tma_out": 2, "gemm_band_mb": 32, "posconv4": 1, "conv0_fold": 1, "attn_blk": 1, "attn_split": 1, "gemm_pair_split": 1, "gemm_pair_min_waves10": 18, "gemm_pair_qkv": 1}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("specs", nargs="+")
