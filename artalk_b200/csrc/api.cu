@@ -190,6 +190,7 @@ int artalk_set_option(const char* name, int value) {
   if (!std::strcmp(name, "gemm_pair_split")) { set_gemm_pair_split(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_pair_min_waves10")) { set_gemm_pair_min_waves10(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_pair_qkv")) { set_gemm_pair_qkv(value); return AT_OK; }
+  if (!std::strcmp(name, "gemm_epi_warps")) { set_gemm_epi_warps(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_tma_out")) { set_gemm_tma_out(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_band_mb")) { set_gemm_band_mb(value); return AT_OK; }
   if (!std::strcmp(name, "gemm_tma_resid")) { set_gemm_tma_resid(value); return AT_OK; }

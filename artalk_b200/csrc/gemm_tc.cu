@@ -697,8 +697,12 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
 // than the epilogue and runs at the 256-wide tile's operand reuse. (A 256 x 128 variant with two stages measured 10 % slower on
 // the whole bf16x3 step: with N = 128 a k-block moves 24 KB into and 32 KB out of shared memory per 256 clk, tensor pipe 40-45 %,
 // profiles/r2_ncu_new_kernels.md.)
-template <int EPI, int RB = 1, int SPLIT2 = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+// NEW = epilogue warps per CTA (8, or 12 for activation epilogues with a bf16-only TMA-store output: their tiles are 2 KB, so twelve
+// warps share the 32 KB scratch): a 256-wide tile's eight 32-column chunks then go to three warps per lane quarter (3 / 3 / 2 chunks
+// instead of 4 / 4) and three epilogue warps per scheduler hide each other's tcgen05.ld and MUFU latencies (FFN1's GELU epilogue
+// held the tensor pipe at 72 %); 128 registers per thread, no spills.
+template <int EPI, int RB = 1, int SPLIT2 = 0, int NEW = 8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEW, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmO, const TcParams p) {
@@ -727,7 +731,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * NEW); }
     for (int i = 0; i < 6; ++i) { mbar_init(rfull_bar(i), 1); mbar_init(rempty_bar(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -849,9 +853,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, 128 rows each) =====================
+    constexpr int NPART = NEW / 4;                       // warps per lane quarter: chunk c goes to part c % NPART
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
     const bool gate_bf = EPI == 1 && p.gate && p.gate_dt == DT_BF16;
-    float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 1024u - smem_u32(smem_raw)) + (warp - 4) * 4096);
+    float4* scr = reinterpret_cast<float4*>(smem_raw + (bar_base + 1024u - smem_u32(smem_raw)) + (warp - 4) * (NEW == 8 ? 4096 : 2048));
     const CUtensorMap* tmo = (EPI != 2 && p.tma_out) ? &tmO : nullptr;
     int it = 0;
     uint32_t r_use = 0;
@@ -868,7 +873,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int64_t g_off = (row_ok && p.gate) ? p.gate_map.off(r) : 0;
       const int64_t r_off = (row_ok && p.resid) ? p.resid_map.off(r) : 0;
       if (EPI == 1 && row_ok && p.vec_ok) {
-        for (int c = half; c < n_chunks; c += 2) {
+        for (int c = half; c < n_chunks; c += NPART) {
           const int col0 = col_base + c * 32;
           if (col0 + 32 > p.N) break;
           if (gate_bf) prefetch_l2(reinterpret_cast<const bf16*>(p.gate) + g_off + col0);
@@ -881,7 +886,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         epi_qkv(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC), bn, col_base, half, row_ok, r, p.bias, scr, lane);
       } else
 #pragma unroll 1
-      for (int c = half; c < n_chunks; c += 2) {
+      for (int c = half; c < n_chunks; c += NPART) {
         const float4* rsm = nullptr;
         const int ridx = half + 2 * (int)(r_use % RB);
         if (EPI == 1 && p.tma_resid) {
@@ -998,20 +1003,20 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap&
   return launch_bn_epi<BN, 0>(tmA, tmW, tmWt, tmO, p, st);
 }
 
-template <int EPI, int RB = 1, int SPLIT2 = 0>
+template <int EPI, int RB = 1, int SPLIT2 = 0, int NEW = 8>
 int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWt, const CUtensorMap& tmR,
                     const CUtensorMap& tmO, const TcParams& p, cudaStream_t st) {
   static int max_clusters_dev[16] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
   int& max_clusters = per_device_slot(max_clusters_dev);
   if (max_clusters < 0) {
-    AT_TRY(ensure_dyn_smem((const void*)gemm_tc2_kernel<EPI, RB, SPLIT2>, SMEM2_BYTES));
+    AT_TRY(ensure_dyn_smem((const void*)gemm_tc2_kernel<EPI, RB, SPLIT2, NEW>, SMEM2_BYTES));
     cudaLaunchConfig_t qc = {};
-    qc.gridDim = dim3(g_num_sms & ~1); qc.blockDim = dim3(384); qc.dynamicSmemBytes = SMEM2_BYTES;
+    qc.gridDim = dim3(g_num_sms & ~1); qc.blockDim = dim3(128 + 32 * NEW); qc.dynamicSmemBytes = SMEM2_BYTES;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.attrs = qa; qc.numAttrs = 1;
     int n = 0;
-    AT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<EPI, RB, SPLIT2>, &qc));
+    AT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc2_kernel<EPI, RB, SPLIT2, NEW>, &qc));
     max_clusters = n > 0 ? n : 1;
     if (getenv("ARTALK_DEBUG")) fprintf(stderr, "[artalk] gemm pair kernel EPI=%d: max active clusters %d (SMs %d)\n", EPI, n, g_num_sms);
     if (max_clusters > g_num_sms / 2) max_clusters = g_num_sms / 2;
@@ -1019,12 +1024,12 @@ int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
   const int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
   g_trace_dims[0] = p.rpb * p.n_batches; g_trace_dims[1] = p.N; g_trace_dims[2] = p.num_kb * BK;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(128 + 32 * NEW); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_on() ? 2 : 1;
-  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI, RB, SPLIT2>, tmA, tmW, tmWt, tmR, tmO, p));
+  AT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<EPI, RB, SPLIT2, NEW>, tmA, tmW, tmWt, tmR, tmO, p));
   AT_LAUNCH_CHECK();
   return AT_OK;
 }
@@ -1036,6 +1041,7 @@ int g_band_mb = 32;       // option "gemm_band_mb": W larger than twice this is 
 int g_pair_split = 1;     // option "gemm_pair_split": parity-grade (piece-block) GEMMs take the CTA-pair kernel (0: the 1-CTA kernel)
 int g_pair_min_waves10 = 18;   // option "gemm_pair_min_waves10": the pair kernel needs at least this many tenths of a wave of 256-row tiles (was 40: 256 x 30 s step 590.0 -> 579.8 ms, bit-identical)
 int g_pair_qkv = 1;       // option "gemm_pair_qkv": the fused q/k/v epilogue GEMMs may take the CTA-pair kernel
+int g_epi_warps = 12;     // option "gemm_epi_warps": epilogue warps of the pair kernel for plain bf16 TMA-store outputs (8 or 12)
 int g_force_bn = 0;       // developer switch: force the 1-CTA kernel's N tile (option "gemm_force_bn")
 
 }  // namespace
@@ -1049,6 +1055,7 @@ void set_gemm_resid_deep(int on) { g_resid_deep = on; }
 void set_gemm_pair_split(int on) { g_pair_split = on; }
 void set_gemm_pair_min_waves10(int v) { g_pair_min_waves10 = v; }
 void set_gemm_pair_qkv(int v) { g_pair_qkv = v; }
+void set_gemm_epi_warps(int v) { g_epi_warps = v; }
 
 int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
   GemmArgs g = g_in;
@@ -1150,6 +1157,9 @@ int launch_gemm_tc(const GemmArgs& g_in, cudaStream_t st) {
       if (p.tma_resid && g_resid_deep >= 2 && p.num_kb <= 16) return launch_pair_epi<1, 3>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (p.tma_resid && g_resid_deep >= 1 && p.num_kb <= 32) return launch_pair_epi<1, 2>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       if (p.gate || p.resid) return launch_pair_epi<1>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
+      // activation epilogues with a bf16-only TMA-store output (FFN1 + GELU of wav2vec / AR / VAE): twelve epilogue warps. Op-level
+      // (tools_opbench.py): FFN1 + GELU 250-255 -> 241-243 us; without an activation (QKV: equal, hoisted AdaLN GEMM: 5 % slower) eight
+      if (g_epi_warps == 12 && p.tma_out == 2 && p.act != ACT_NONE) return launch_pair_epi<0, 1, 0, 12>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
       return launch_pair_epi<0>(tmA2, tmW2, tmW2t, tmR, tmO, p, st);
     }
   }

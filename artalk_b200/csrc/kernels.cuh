@@ -88,6 +88,7 @@ void set_gemm_resid_deep(int on);
 void set_gemm_pair_split(int on);
 void set_gemm_pair_min_waves10(int v);
 void set_gemm_pair_qkv(int v);
+void set_gemm_epi_warps(int v);
 // skinny-M bf16 GEMM (mma.sync, cp.async ring; M <= option "skinny_max_m") for the latency-bound steps. skinny.cu
 bool gemm_skinny_supported(const GemmArgs& g);
 int launch_gemm_skinny(const GemmArgs& g, cudaStream_t st);

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from artalk_b200 import _lib, config, synthetic
 from artalk_b200.engine import ARTAvatarInferEngine
 
-DEFAULTS = {"attn_bound": 1, "w2v_graph_chunks": 4, "skinny_tokens": 1, "pdl_mask": 3, "gemm_pair": 1, "gemm_tma_out": 2, "gemm_band_mb": 32, "posconv4": 1, "conv0_fold": 1, "attn_blk": 1, "attn_split": 1, "gemm_pair_split": 1, "gemm_pair_min_waves10": 18, "gemm_pair_qkv": 1}
+DEFAULTS = {"attn_bound": 1, "w2v_graph_chunks": 4, "skinny_tokens": 1, "pdl_mask": 3, "gemm_pair": 1, "gemm_tma_out": 2, "gemm_band_mb": 32, "posconv4": 1, "conv0_fold": 1, "attn_blk": 1, "attn_split": 1, "gemm_pair_split": 1, "gemm_pair_min_waves10": 18, "gemm_pair_qkv": 1, "gemm_epi_warps": 12}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("specs", nargs="+")
