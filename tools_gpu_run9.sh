@@ -3,7 +3,7 @@
 # reference arm, contract-parity line, launch list of the bench command.
 set -x
 cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
-TAG=${TAG:-r2x}
+TAG=${TAG:-r2fin}
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader > gpurun_out/${TAG}_gpu.txt
 timeout 1200 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"
 tail -4 gpurun_out/${TAG}_pytest.log | cut -c1-300
