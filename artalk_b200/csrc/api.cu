@@ -24,6 +24,18 @@ int artalk_create(const artalk_config_t* cfg, artalk_engine_t** out) {
   artalk_engine* e = new (std::nothrow) artalk_engine();
   if (!e) return AT_ENOMEM;
   std::memcpy(&e->eng.cfg, cfg, sizeof(EngineConfig));
+  // wav2vec sub-batch budget: 45 % of the device's memory, at most 80 GiB (a B200 then encodes the 2048 chunks of 256 x 30 s in one
+  // sub-batch of 66 GB instead of three: 577 -> 571 ms per step); the arena itself only grows to what a call needs
+  // (the piece-block modes keep the 24 GiB default: their operand-split buffers grow with the sub-batch, 49 GB for conv layer 1 at
+  // 1250 chunks)
+  size_t free_b = 0, total_b = 0;
+  if (e->eng.cfg.precision >= 2) {
+  } else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) {
+    const size_t cap = (size_t)80 << 30, share = (size_t)((double)total_b * 0.45);
+    e->eng.ws_limit = share < cap ? share : cap;
+  } else {
+    cudaGetLastError();
+  }
   *out = e;
   return AT_OK;
 }

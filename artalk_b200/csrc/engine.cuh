@@ -34,7 +34,7 @@ struct Engine {
   bool finalized = false;
   // workspace
   char* ws = nullptr; size_t ws_cap = 0; size_t ws_off = 0;
-  size_t ws_limit = (size_t)24 << 30;     // soft budget used to size wav2vec sub-batches
+  size_t ws_limit = (size_t)24 << 30;     // soft budget used to size wav2vec sub-batches (artalk_create: 45 % of device memory, <= 80 GiB)
   BitsTables tb;
   // derived
   int L = 0, T = 0, n_audio_frames = 0; int conv_len[8];
