@@ -248,7 +248,10 @@ def test_inference_bf16_teacher_forced(name):
     gold_prev = torch.from_numpy(g["prev_bits"].view(np.int32).copy())
     out = m.inference({"audio": case.audio(), "style_motion": case.style()}, trace=tr, teacher_words=gold_words,
                       teacher_prev_words=gold_prev)
-    err = np.abs(tr["logits"].cpu().numpy() - g["logits"])
+    diff = tr["logits"].cpu().numpy() - g["logits"]
+    err = np.abs(diff)
+    bias = float(diff.mean())                                       # a systematic error (wrong offset / fit) shows here, noise does not
+    pair_bias = float((diff[..., 1::2] - diff[..., 0::2]).mean())   # ... and here if it leaned the pairwise decisions one way
     mg = gu.margins(g["logits"])
     bits = unpack_words(tr["words"]).cpu()
     gb = gu.unpack_bits(g["bits"])
@@ -257,10 +260,13 @@ def test_inference_bf16_teacher_forced(name):
     merr = np.abs(out.cpu().numpy() - g["motion"]).max()
     _record("bf16_teacher_forced", dict(case=name, logit_max=float(err.max()), logit_mean=float(err.mean()), flips=int(flips.sum()),
                                         flip_rate=float(flips.float().mean()), max_margin_of_flip=float(mg[flips].max()) if flips.any() else 0.0,
-                                        motion_max=float(merr), prev_flip_frac=prev_frac))
+                                        motion_max=float(merr), prev_flip_frac=prev_frac, logit_bias=bias, logit_pair_bias=pair_bias))
     # measured on B200 (round 2, full_10s): logits max 0.097 / mean 0.0147, 66 of 17 376 bits flipped (0.38 %), largest reference
     # margin among the flipped bits 0.077, motion max 0.017. Thresholds = those values with ~2x headroom
     assert err.max() < BF16_LOGIT_MAX and err.mean() < BF16_LOGIT_MEAN, (err.max(), err.mean())
+    # the error is noise, not an offset: mean signed error 0.02-0.09 of the mean absolute error (measured), and the pairwise
+    # differences that decide the bits lean neither way (<= 0.08 of it); a wrong gate offset or activation fit would show here
+    assert abs(bias) < 0.3 * err.mean() and abs(pair_bias) < 0.25 * err.mean(), (bias, pair_bias, err.mean())
     assert int((flips & (mg > BF16_BIT_MARGIN)).sum()) == 0
     assert flips.float().mean().item() < BF16_FLIP_RATE
     # given the same bits in, every chunk's decode is within the bf16 tolerance of the reference
